@@ -1,0 +1,132 @@
+"""Device (B200) implementation of online / offline SGD matrix factorisation.
+
+Capability parity with ``PSOnlineMatrixFactorization.psOnlineMF`` and
+``PSOfflineMatrixFactorization.psOfflineMF`` (reference:
+M/matrix/factorization/PSOnlineMatrixFactorization.scala:39-75,
+M/matrix/factorization/workers/PSOnlineMatrixFactorizationWorker.scala:22-90):
+
+* user vectors live on the *worker* that owns the user (``user % workerParallelism``),
+* item vectors live on the parameter server, sharded ``item % psParallelism``,
+* every rating triggers pull(item) -> SGD delta -> local user update -> push(item delta).
+
+B200-first mechanism: one process per GPU is both worker ``rank`` and PS shard ``rank``; the whole
+worker step for a micro-batch is ONE kernel (``fps_mf_sgd_fused``) that pulls item rows with
+16-byte loads from the owner's HBM over NVSwitch, computes the update and pushes the delta back
+with ``red.global.add.v4.f32`` -- no messages, no NCCL, no separate elementwise kernel.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ...ops import native
+from ...runtime.device_stream import DevicePrefetcher
+from ...store.sharded_table import ShardedTable
+
+ERR_SIGMOID = 0  # reference parity: e = sigmoid(r - u.v)   (SGDUpdater.scala:8)
+ERR_PLAIN = 1    # textbook SGD:     e = r - u.v
+
+DEFAULT_DEVICE_PULL_LIMIT = 0  # 0 = as many row slots in flight as the GPU can hold
+
+
+class DeviceOnlineMF:
+    def __init__(self, num_users: int, num_items: int, num_factors: int = 10,
+                 range_min: float = -0.01, range_max: float = 0.01, learning_rate: float = 0.01,
+                 negative_sample_rate: int = 0, pull_limit: int = DEFAULT_DEVICE_PULL_LIMIT,
+                 group=None, seed: int = 0, err_mode: int = ERR_SIGMOID,
+                 device: Optional[int] = None, track_touched: bool = False):
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.cuda_device = torch.device("cuda", self.device)
+        self.group = group
+        ready = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ready else 1
+        self.rank = dist.get_rank(group) if ready else 0
+        self.num_users, self.num_items, self.k = int(num_users), int(num_items), int(num_factors)
+        self.lr = float(learning_rate)
+        self.neg = int(negative_sample_rate)
+        self.pull_limit = int(pull_limit)
+        self.err_mode = int(err_mode)
+        self.seed = int(seed)
+        self.step_no = 0
+        with torch.cuda.device(self.device):
+            # parameter server: item vectors, sharded item % psParallelism
+            self.items = ShardedTable(num_items, num_factors, partition="hash", group=group,
+                                      device=self.device, init="uniform",
+                                      init_range=(range_min, range_max), seed=seed * 2 + 1,
+                                      track_touched=track_touched)
+            # worker-local state: vectors of the users this worker owns (user % W == rank)
+            n_local = -(-self.num_users // self.world)
+            self.users = torch.empty((n_local, self.items.stride), dtype=torch.float32,
+                                     device=self.cuda_device)
+            native.init_rows(self.users, self.k, self.rank, self.world, native.PART_HASH, n_local,
+                             seed * 2 + 2, range_min, range_max)
+            self.stats = torch.zeros(2, dtype=torch.float32, device=self.cuda_device)
+            self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.cuda_device)
+        self.items.barrier()
+
+    # ------------------------------------------------------------------------------------
+    def step(self, users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor) -> None:
+        """Process one micro-batch of ratings whose users belong to this worker (async SGD)."""
+        native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
+                            self.lr, err_mode=self.err_mode, neg_rate=self.neg,
+                            num_items=self.num_items, seed=self.seed, step=self.step_no,
+                            stats=self.stats, nan_flag=self.nan_flag,
+                            max_inflight_rows=self.pull_limit)
+        self.step_no += 1
+
+    def fit_stream(self, host_batches: Iterable[Sequence[torch.Tensor]],
+                   loss_every: int = 1):
+        """End-to-end training over pinned host micro-batches ``(users, items, ratings)``.
+
+        Yields one host-side ``(sum_sq_err, n_updates)`` per micro-batch (device -> host read of
+        the step's result), lagging the launch by one step so copies, kernels and reads overlap.
+        """
+        pf = DevicePrefetcher(host_batches, self.cuda_device, depth=2)
+        self.prefetcher = pf
+        pending = []
+        ring = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(4)]
+        i = 0
+        for (u, it, r) in pf:
+            self.stats.zero_()
+            self.step(u, it, r)
+            host = ring[i % len(ring)]
+            host.copy_(self.stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((host, ev))
+            i += 1
+            if len(pending) > 2:
+                h, e = pending.pop(0)
+                e.synchronize()
+                yield float(h[0]), float(h[1])
+        for h, e in pending:
+            e.synchronize()
+            yield float(h[0]), float(h[1])
+
+    # -- quality / export -------------------------------------------------------------------
+    def predict(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+        """u.v for (user, item) pairs whose users are local (pull fused with the dot)."""
+        slots = (users.to(torch.int64) // self.world)
+        local = self.users[slots].contiguous()
+        return self.items.pull_dot(items, local)
+
+    def user_vectors(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        n_local = self.users.shape[0]
+        ids = torch.arange(n_local, device=self.cuda_device) * self.world + self.rank
+        sel = ids < self.num_users
+        return ids[sel], self.users[sel, : self.k].clone()
+
+    def item_vectors(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.items.dump_local()
+
+    def check_finite(self) -> None:
+        if int(self.nan_flag.item()) != 0:
+            raise FloatingPointError("non-finite SGD update (FactorIsNotANumberException)")
+
+    def barrier(self) -> None:
+        self.items.barrier()
+
+    def close(self) -> None:
+        self.items.close()

@@ -1,0 +1,407 @@
+// Core parameter-server kernels for sm_100a: lazy-init materialisation (K4), fused
+// pull + SGD + push for matrix factorisation (K1+K3+K2), standalone pull gather (K1),
+// push accumulate (K2) and pull-fused-with-dot scoring.  All "communication" is done by
+// the kernels themselves through peer-mapped shard pointers (NVLink/NVSwitch one-sided
+// loads and REDG.ADD.F32x4 reductions); no NCCL call sits on these paths.
+//
+// Reference behaviour being reproduced (not code): SimplePSLogic.scala:13-25 (init on
+// first pull, additive update), SGDUpdater.scala:5-14 (delta rule),
+// PSOnlineMatrixFactorizationWorker.scala:42-89 (worker step + negative sampling).
+#include "fps_common.cuh"
+
+// ----------------------------------------------------------------------------------------
+// K4: materialise rows as a pure function of (seed, id, column).
+//   value(id, j) = lo + (hi - lo) * u01(philox(id_lo, id_hi, j / 4, 0; seed_lo, seed_hi)[j % 4])
+// "init on first pull" (RangedRandomFactorInitializer.scala:7-9, PseudoRandomFactorInitializer
+// .scala:9-12) becomes "every slot already holds what init(id) would return".
+// ----------------------------------------------------------------------------------------
+__global__ void fps_init_rows_kernel(float* __restrict__ rows, long long n_rows, int dim,
+                                     int stride, int shard, int num_shards, int mode,
+                                     long long div, unsigned long long seed, float lo,
+                                     float hi) {
+  const int nvec = stride >> 2;
+  const long long total = n_rows * nvec;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long slot = t / nvec;
+    const int q = (int)(t - slot * nvec);
+    const long long id = (mode == FPS_PART_HASH) ? slot * num_shards + shard
+                                                 : (long long)shard * div + slot;
+    Philox4 r = fps_philox((uint32_t)id, (uint32_t)((unsigned long long)id >> 32), (uint32_t)q,
+                           0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float4 v;
+    const float sc = hi - lo;
+    v.x = (4 * q + 0 < dim) ? lo + sc * fps_u01(r.x) : 0.f;
+    v.y = (4 * q + 1 < dim) ? lo + sc * fps_u01(r.y) : 0.f;
+    v.z = (4 * q + 2 < dim) ? lo + sc * fps_u01(r.z) : 0.f;
+    v.w = (4 * q + 3 < dim) ? lo + sc * fps_u01(r.w) : 0.f;
+    *reinterpret_cast<float4*>(rows + slot * (long long)stride + 4 * q) = v;
+  }
+}
+
+extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride, int shard,
+                             int num_shards, int mode, long long div, unsigned long long seed,
+                             float lo, float hi, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  long long total = n_rows * (stride / 4);
+  int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  fps_init_rows_kernel<<<(int)blocks, threads, 0, stream>>>(rows, n_rows, dim, stride, shard,
+                                                            num_shards, mode, div, seed, lo, hi);
+  return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------
+// K1+K3+K2: fused matrix-factorisation step.
+//   for each (user, item, rating):          [+ neg_rate sampled (user, item', 0)]
+//     v  = pull(item)      -- 16-byte loads from the owning shard (local HBM or NVLink peer)
+//     u  = user row (worker-local HBM)
+//     e  = err_mode==0 ? sigmoid(r - u.v) : (r - u.v)     (SGDUpdater.scala:8)
+//     u += lr*e*v          -- local REDG.ADD.F32x4 (no lost updates inside a micro-batch)
+//     push(item, lr*e*u)   -- REDG.ADD.F32x4 to the owner == paramUpdate(vectorSum) applied
+//                              by the owner's memory system
+// LPR lanes cooperate on one row (each lane owns VPL float4 chunks); each lane-group keeps R
+// ratings in flight so the peer-load latency (~2 us over NVSwitch) is covered by ILP.
+// The pull limiter (WL:196-250) is the number of row slots in flight: grid * 256 / LPR * R,
+// chosen by the host from pullLimit (credits pre-distributed to resident lane-groups).
+// ----------------------------------------------------------------------------------------
+struct MfArgs {
+  const void* users;
+  const void* items;
+  const float* ratings;
+  long long n_pos;
+  int neg_rate;
+  long long num_items;        // negative-sample id range [0, num_items)
+  unsigned long long seed;    // negative-sample stream key
+  unsigned long long step;    // negative-sample stream counter (micro-batch number)
+  float* user_table;          // worker-local [n_local_users, stride]
+  int user_div;               // workerParallelism: local slot = user / user_div
+  float lr;
+  int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual
+  float* stats;               // [0] += sum (r-u.v)^2, [1] += #updates
+  int* nan_flag;              // set to 1 if a non-finite update was produced
+  ShardTable item_tab;
+};
+
+template <typename IdT, int LPR, int VPL, int R>
+__global__ void __launch_bounds__(256)
+    fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int per_pos = 1 + a.neg_rate;
+  const long long n_eff = a.n_pos * per_pos;
+  const int nvec = a.item_tab.stride >> 2;
+  const IdT* __restrict__ users = reinterpret_cast<const IdT*>(a.users);
+  const IdT* __restrict__ items = reinterpret_cast<const IdT*>(a.items);
+  float sq_acc = 0.f, cnt_acc = 0.f;
+  bool bad = false;
+
+  for (long long base = 0; base < n_eff; base += n_groups * R) {
+    float4 u[R][VPL], v[R][VPL];
+    float* up[R];
+    float* vp[R];
+    float rt[R];
+    bool ok[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long idx = base + (long long)r * n_groups + group;
+      ok[r] = idx < n_eff;
+      long long pos = idx;
+      int j = 0;
+      if (per_pos > 1) {
+        pos = idx / per_pos;
+        j = (int)(idx - pos * per_pos);
+      }
+      long long user = 0, item = 0;
+      rt[r] = 0.f;
+      if (ok[r]) {
+        user = (long long)users[pos];
+        item = (long long)items[pos];
+        if (j == 0) {
+          rt[r] = a.ratings[pos];
+        } else {
+          // K5: device-side negative sample, rejecting the positive item itself.
+          Philox4 s = fps_philox((uint32_t)pos, (uint32_t)((unsigned long long)pos >> 32),
+                                 (uint32_t)j, (uint32_t)a.step, (uint32_t)a.seed,
+                                 (uint32_t)(a.seed >> 32));
+          unsigned long long h = ((unsigned long long)s.x << 32) | s.y;
+          long long neg = (long long)(h % (unsigned long long)a.num_items);
+          if (neg == item) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
+          item = neg;
+        }
+      }
+      up[r] = a.user_table + (user / a.user_div) * (long long)a.item_tab.stride;
+      vp[r] = fps_row(a.item_tab, item);
+#pragma unroll
+      for (int c = 0; c < VPL; ++c) {
+        const int q = lane + c * LPR;
+        if (ok[r] && q < nvec) {
+          v[r][c] = fps_ld_row4(vp[r] + 4 * q);  // the PULL
+          u[r][c] = *reinterpret_cast<const float4*>(up[r] + 4 * q);
+        } else {
+          v[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          u[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < VPL; ++c)
+        d += u[r][c].x * v[r][c].x + u[r][c].y * v[r][c].y + u[r][c].z * v[r][c].z +
+             u[r][c].w * v[r][c].w;
+      d = fps_group_sum<LPR>(d);
+      const float resid = rt[r] - d;
+      const float e = (a.err_mode == 0) ? 1.f / (1.f + __expf(-resid)) : resid;
+      const float g = a.lr * e;
+      if (ok[r]) {
+        if (!(fabsf(g) <= 3.0e38f)) bad = true;  // NaN/Inf guard (Vector.scala:78-80)
+        if (lane == 0) {
+          sq_acc += resid * resid;
+          cnt_acc += 1.f;
+        }
+#pragma unroll
+        for (int c = 0; c < VPL; ++c) {
+          const int q = lane + c * LPR;
+          if (q < nvec) {
+            float4 du = make_float4(g * v[r][c].x, g * v[r][c].y, g * v[r][c].z, g * v[r][c].w);
+            float4 dv = make_float4(g * u[r][c].x, g * u[r][c].y, g * u[r][c].z, g * u[r][c].w);
+            fps_red_add4(up[r] + 4 * q, du);   // worker-local user update
+            fps_red_add4(vp[r] + 4 * q, dv);   // the PUSH, fused with paramUpdate
+          }
+        }
+      }
+    }
+  }
+  // statistics: one atomic pair per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sq_acc += __shfl_xor_sync(0xffffffffu, sq_acc, o);
+    cnt_acc += __shfl_xor_sync(0xffffffffu, cnt_acc, o);
+  }
+  if ((threadIdx.x & 31) == 0 && a.stats != nullptr && cnt_acc > 0.f) {
+    atomicAdd(a.stats + 0, sq_acc);
+    atomicAdd(a.stats + 1, cnt_acc);
+  }
+  if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
+}
+
+template <typename IdT, int LPR, int VPL, int R>
+static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
+  const int threads = 256;
+  const int groups_per_block = threads / LPR;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R>,
+                                                threads, 0);
+  if (occ < 1) occ = 1;
+  long long blocks = (long long)num_sms * occ;
+  // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
+  if (max_inflight_rows > 0) {
+    long long cap = max_inflight_rows / ((long long)groups_per_block * R);
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+  }
+  const long long n_eff = a.n_pos * (1 + a.neg_rate);
+  long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
+  if (need < 1) need = 1;
+  if (blocks > need) blocks = need;
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R><<<(int)blocks, threads, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <typename IdT>
+static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
+  const int nvec = a.item_tab.stride >> 2;
+  if (nvec <= 1) return launch_mf<IdT, 1, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 2) return launch_mf<IdT, 2, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 4) return launch_mf<IdT, 4, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 8) return launch_mf<IdT, 8, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 16) return launch_mf<IdT, 16, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 32) return launch_mf<IdT, 32, 1, 4>(a, max_inflight, num_sms, s);
+  if (nvec <= 64) return launch_mf<IdT, 32, 2, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 96) return launch_mf<IdT, 32, 3, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 128) return launch_mf<IdT, 32, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 256) return launch_mf<IdT, 32, 8, 1>(a, max_inflight, num_sms, s);
+  return -1000;  // dim > 1024 not supported by the fused MF kernel
+}
+
+extern "C" int fps_mf_sgd_fused(const MfArgs* args, int id_bytes, int max_inflight_rows,
+                                int num_sms, cudaStream_t stream) {
+  if (args->n_pos <= 0) return 0;
+  if (id_bytes == 4) return dispatch_mf<int>(*args, max_inflight_rows, num_sms, stream);
+  if (id_bytes == 8) return dispatch_mf<long long>(*args, max_inflight_rows, num_sms, stream);
+  return -1001;
+}
+
+// ----------------------------------------------------------------------------------------
+// K1 standalone: out[i, :] = table[ids[i], :]   (pull for the generic tensor tier)
+// K2 standalone: table[ids[i], :] += delta[i, :] (push fused with additive paramUpdate)
+// pull_dot:      score[i] = table[ids[i], :] . local[i, :]   (pull fused with the consumer)
+// One lane-group of LPR lanes per row, VPL chunks per lane, generic in dim via nvec bound.
+// ----------------------------------------------------------------------------------------
+template <typename IdT, int LPR>
+__global__ void __launch_bounds__(256)
+    fps_pull_gather_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
+                           long long n, float* __restrict__ out, int out_stride, int touch) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int nvec = t.stride >> 2;
+  for (long long i = group; i < n; i += n_groups) {
+    const long long id = (long long)ids[i];
+    const float* src = fps_row(t, id);
+    if (touch && lane == 0) fps_touch(t, id);
+    for (int q = lane; q < nvec; q += LPR) {
+      float4 v = fps_ld_row4(src + 4 * q);
+      float* o = out + i * (long long)out_stride + 4 * q;
+      if ((out_stride & 3) == 0 && 4 * q + 3 < out_stride) {
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        if (4 * q + 0 < out_stride) o[0] = v.x;
+        if (4 * q + 1 < out_stride) o[1] = v.y;
+        if (4 * q + 2 < out_stride) o[2] = v.z;
+        if (4 * q + 3 < out_stride) o[3] = v.w;
+      }
+    }
+  }
+}
+
+template <typename IdT, int LPR>
+__global__ void __launch_bounds__(256)
+    fps_push_add_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
+                        long long n, const float* __restrict__ delta, int delta_stride, float scale,
+                        int touch, int* nan_flag) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int nvec = t.stride >> 2;
+  bool bad = false;
+  for (long long i = group; i < n; i += n_groups) {
+    const long long id = (long long)ids[i];
+    float* dst = fps_row(t, id);
+    if (touch && lane == 0) fps_touch(t, id);
+    for (int q = lane; q < nvec; q += LPR) {
+      const float* d = delta + i * (long long)delta_stride + 4 * q;
+      float4 v;
+      if (4 * q + 3 < delta_stride && (delta_stride & 3) == 0) {
+        v = *reinterpret_cast<const float4*>(d);
+      } else {
+        v.x = (4 * q + 0 < delta_stride) ? d[0] : 0.f;
+        v.y = (4 * q + 1 < delta_stride) ? d[1] : 0.f;
+        v.z = (4 * q + 2 < delta_stride) ? d[2] : 0.f;
+        v.w = (4 * q + 3 < delta_stride) ? d[3] : 0.f;
+      }
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      if (!(fabsf(v.x) <= 3.0e38f) || !(fabsf(v.y) <= 3.0e38f) || !(fabsf(v.z) <= 3.0e38f) ||
+          !(fabsf(v.w) <= 3.0e38f))
+        bad = true;
+      fps_red_add4(dst + 4 * q, v);
+    }
+  }
+  if (bad && nan_flag != nullptr) *nan_flag = 1;
+}
+
+template <typename IdT, int LPR>
+__global__ void __launch_bounds__(256)
+    fps_pull_dot_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
+                        long long n, const float* __restrict__ local, int local_stride,
+                        float* __restrict__ score) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int nvec = t.stride >> 2;
+  const long long n_round = ((n + n_groups - 1) / n_groups) * n_groups;
+  for (long long i = group; i < n_round; i += n_groups) {
+    float d = 0.f;
+    if (i < n) {
+      const float* src = fps_row(t, (long long)ids[i]);
+      for (int q = lane; q < nvec; q += LPR) {
+        float4 v = fps_ld_row4(src + 4 * q);
+        const float* l = local + i * (long long)local_stride + 4 * q;
+        float4 w;
+        w.x = (4 * q + 0 < local_stride) ? l[0] : 0.f;
+        w.y = (4 * q + 1 < local_stride) ? l[1] : 0.f;
+        w.z = (4 * q + 2 < local_stride) ? l[2] : 0.f;
+        w.w = (4 * q + 3 < local_stride) ? l[3] : 0.f;
+        d += v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+      }
+    }
+    d = fps_group_sum<LPR>(d);
+    if (i < n && lane == 0) score[i] = d;
+  }
+}
+
+static inline int pick_lpr(int nvec) {
+  int l = 1;
+  while (l < nvec && l < 32) l <<= 1;
+  return l;
+}
+static inline int row_grid(long long n, int lpr, int num_sms) {
+  long long groups_per_block = 256 / lpr;
+  long long blocks = (n + groups_per_block - 1) / groups_per_block;
+  long long cap = (long long)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+#define FPS_DISPATCH_LPR(KERNEL, IDT, LPRV, GRID, STREAM, ...)                               \
+  switch (LPRV) {                                                                            \
+    case 1: KERNEL<IDT, 1><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                    \
+    case 2: KERNEL<IDT, 2><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                    \
+    case 4: KERNEL<IDT, 4><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                    \
+    case 8: KERNEL<IDT, 8><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                    \
+    case 16: KERNEL<IDT, 16><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                  \
+    default: KERNEL<IDT, 32><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                  \
+  }
+
+extern "C" int fps_pull_gather(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                               float* out, int out_stride, int touch, int num_sms,
+                               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int lpr = pick_lpr(t->stride >> 2);
+  const int grid = row_grid(n, lpr, num_sms);
+  if (id_bytes == 4) {
+    FPS_DISPATCH_LPR(fps_pull_gather_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, out,
+                     out_stride, touch)
+  } else {
+    FPS_DISPATCH_LPR(fps_pull_gather_kernel, long long, lpr, grid, stream, *t,
+                     (const long long*)ids, n, out, out_stride, touch)
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int fps_push_add(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                            const float* delta, int delta_stride, float scale, int touch,
+                            int* nan_flag, int num_sms, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int lpr = pick_lpr(t->stride >> 2);
+  const int grid = row_grid(n, lpr, num_sms);
+  if (id_bytes == 4) {
+    FPS_DISPATCH_LPR(fps_push_add_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, delta,
+                     delta_stride, scale, touch, nan_flag)
+  } else {
+    FPS_DISPATCH_LPR(fps_push_add_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
+                     n, delta, delta_stride, scale, touch, nan_flag)
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int fps_pull_dot(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                            const float* local, int local_stride, float* score, int num_sms,
+                            cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int lpr = pick_lpr(t->stride >> 2);
+  const int grid = row_grid(n, lpr, num_sms);
+  if (id_bytes == 4) {
+    FPS_DISPATCH_LPR(fps_pull_dot_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, local,
+                     local_stride, score)
+  } else {
+    FPS_DISPATCH_LPR(fps_pull_dot_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
+                     n, local, local_stride, score)
+  }
+  return (int)cudaGetLastError();
+}

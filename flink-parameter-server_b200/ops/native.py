@@ -1,0 +1,267 @@
+"""ctypes bindings for ``libfps_kernels.so`` (hand-written sm_100a kernels + fabric).
+
+Every wrapper takes torch CUDA tensors, validates them, and launches on the *current* torch
+CUDA stream, so launches compose with torch streams, events and CUDA-graph capture.  There is
+no PyTorch fallback on a GPU box: if the library is missing the ops raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+FPS_MAX_SHARDS = 16
+PART_HASH = 0
+PART_RANGE = 1
+
+_lib = None
+_lib_lock = threading.Lock()
+_launch_count = 0  # number of fps kernels launched by this process (bench "gpu_launches")
+
+
+class ShardTableC(C.Structure):
+    """Mirror of ``struct ShardTable`` (csrc/fps_common.cuh)."""
+
+    _fields_ = [
+        ("base", C.c_void_p * FPS_MAX_SHARDS),
+        ("touched", C.c_void_p * FPS_MAX_SHARDS),
+        ("rows_per_shard", C.c_longlong),
+        ("div", C.c_longlong),
+        ("num_shards", C.c_int),
+        ("dim", C.c_int),
+        ("stride", C.c_int),
+        ("mode", C.c_int),
+    ]
+
+
+class MfArgsC(C.Structure):
+    """Mirror of ``struct MfArgs`` (csrc/fps_core.cu)."""
+
+    _fields_ = [
+        ("users", C.c_void_p),
+        ("items", C.c_void_p),
+        ("ratings", C.c_void_p),
+        ("n_pos", C.c_longlong),
+        ("neg_rate", C.c_int),
+        ("num_items", C.c_longlong),
+        ("seed", C.c_ulonglong),
+        ("step", C.c_ulonglong),
+        ("user_table", C.c_void_p),
+        ("user_div", C.c_int),
+        ("lr", C.c_float),
+        ("err_mode", C.c_int),
+        ("stats", C.c_void_p),
+        ("nan_flag", C.c_void_p),
+        ("item_tab", ShardTableC),
+    ]
+
+
+def available() -> bool:
+    return _build.KERNEL_LIB.exists()
+
+
+def lib() -> C.CDLL:
+    """Load (building if needed) the kernel library.  Raises if it cannot be produced."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.KERNEL_LIB
+        if not path.exists() or os.environ.get("FPS_REBUILD") == "1":
+            _build.build_kernels()
+        l = C.CDLL(str(path))
+        l.fps_error_string.restype = C.c_char_p
+        l.fps_error_string.argtypes = [C.c_int]
+        _lib = l
+    return _lib
+
+
+def launch_count() -> int:
+    return _launch_count
+
+
+def reset_launch_count() -> None:
+    global _launch_count
+    _launch_count = 0
+
+
+def _check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().fps_error_string(int(code))
+        raise RuntimeError(f"fps_b200 native call {what} failed: [{code}] {msg.decode() if msg else ''}")
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_sm_cache = {}
+
+
+def sm_count(device: Optional[int] = None) -> int:
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _sm_cache:
+        _sm_cache[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _sm_cache[dev]
+
+
+def _id_bytes(ids: torch.Tensor) -> int:
+    if ids.dtype == torch.int32:
+        return 4
+    if ids.dtype == torch.int64:
+        return 8
+    raise TypeError(f"ids must be int32 or int64, got {ids.dtype}")
+
+
+def _req(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _bump(n: int = 1) -> None:
+    global _launch_count
+    _launch_count += n
+
+
+# --------------------------------------------------------------------------------------------
+# fabric
+# --------------------------------------------------------------------------------------------
+def heap_alloc(nbytes: int) -> int:
+    out = C.c_void_p()
+    _check(lib().fps_heap_alloc(C.c_size_t(nbytes), C.byref(out)), "heap_alloc")
+    return int(out.value)
+
+
+def heap_free(ptr: int) -> None:
+    _check(lib().fps_heap_free(C.c_void_p(ptr)), "heap_free")
+
+
+def ipc_get_handle(ptr: int) -> bytes:
+    buf = (C.c_ubyte * 64)()
+    _check(lib().fps_ipc_get_handle(C.c_void_p(ptr), buf), "ipc_get_handle")
+    return bytes(buf)
+
+
+def ipc_open_handle(handle: bytes) -> int:
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    out = C.c_void_p()
+    _check(lib().fps_ipc_open_handle(buf, C.byref(out)), "ipc_open_handle")
+    return int(out.value)
+
+
+def ipc_close(ptr: int) -> None:
+    _check(lib().fps_ipc_close(C.c_void_p(ptr)), "ipc_close")
+
+
+def enable_peer(dev: int, peer: int) -> None:
+    _check(lib().fps_enable_peer(int(dev), int(peer)), f"enable_peer({dev},{peer})")
+
+
+class _RawCudaBuffer:
+    """Expose a raw device allocation through ``__cuda_array_interface__`` (zero-copy view)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape),
+            "typestr": typestr,
+            "data": (int(ptr), False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+_TYPESTR = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1",
+            torch.float16: "<f2", torch.int16: "<i2"}
+
+
+def tensor_from_ptr(ptr: int, shape, dtype: torch.dtype, device: int) -> torch.Tensor:
+    """Zero-copy torch view of raw device memory (the owner keeps the allocation alive)."""
+    if dtype == torch.bfloat16:
+        t = torch.as_tensor(_RawCudaBuffer(ptr, shape, "<i2"), device=torch.device("cuda", device))
+        return t.view(torch.bfloat16)
+    return torch.as_tensor(_RawCudaBuffer(ptr, shape, _TYPESTR[dtype]),
+                           device=torch.device("cuda", device))
+
+
+# --------------------------------------------------------------------------------------------
+# kernels
+# --------------------------------------------------------------------------------------------
+def init_rows(rows: torch.Tensor, dim: int, shard: int, num_shards: int, mode: int, div: int,
+              seed: int, lo: float, hi: float) -> None:
+    _req(rows, "rows", torch.float32)
+    n_rows, stride = rows.shape
+    assert stride % 4 == 0
+    _check(lib().fps_init_rows(C.c_void_p(rows.data_ptr()), C.c_longlong(n_rows), int(dim),
+                               int(stride), int(shard), int(num_shards), int(mode),
+                               C.c_longlong(div), C.c_ulonglong(seed & (2**64 - 1)),
+                               C.c_float(lo), C.c_float(hi), _stream()), "init_rows")
+    _bump()
+
+
+def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor,
+                 user_table: torch.Tensor, user_div: int, item_tab: ShardTableC, lr: float,
+                 err_mode: int = 0, neg_rate: int = 0, num_items: int = 0, seed: int = 0,
+                 step: int = 0, stats: Optional[torch.Tensor] = None,
+                 nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0) -> None:
+    """Fused pull + SGD + push (K1+K3+K2).  See csrc/fps_core.cu."""
+    _req(users, "users"); _req(items, "items"); _req(ratings, "ratings", torch.float32)
+    _req(user_table, "user_table", torch.float32)
+    if users.dtype != items.dtype:
+        raise TypeError("users and items must share an integer dtype")
+    if user_table.shape[1] != item_tab.stride:
+        raise ValueError("user table stride must equal item table stride")
+    a = MfArgsC()
+    a.users = users.data_ptr(); a.items = items.data_ptr(); a.ratings = ratings.data_ptr()
+    a.n_pos = users.numel(); a.neg_rate = int(neg_rate); a.num_items = int(max(num_items, 1))
+    a.seed = seed & (2**64 - 1); a.step = int(step)
+    a.user_table = user_table.data_ptr(); a.user_div = int(user_div)
+    a.lr = float(lr); a.err_mode = int(err_mode)
+    a.stats = stats.data_ptr() if stats is not None else None
+    a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
+    a.item_tab = item_tab
+    _check(lib().fps_mf_sgd_fused(C.byref(a), _id_bytes(users), int(max_inflight_rows),
+                                  sm_count(users.device.index), _stream()), "mf_sgd_fused")
+    _bump()
+
+
+def pull_gather(tab: ShardTableC, ids: torch.Tensor, out: torch.Tensor, touch: bool = False) -> None:
+    _req(ids, "ids"); _req(out, "out", torch.float32)
+    assert out.shape[0] == ids.numel() and out.shape[1] <= tab.stride
+    _check(lib().fps_pull_gather(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
+                                 C.c_longlong(ids.numel()), C.c_void_p(out.data_ptr()),
+                                 int(out.shape[1]), int(bool(touch)), sm_count(ids.device.index),
+                                 _stream()), "pull_gather")
+    _bump()
+
+
+def push_add(tab: ShardTableC, ids: torch.Tensor, delta: torch.Tensor, scale: float = 1.0,
+             touch: bool = False, nan_flag: Optional[torch.Tensor] = None) -> None:
+    _req(ids, "ids"); _req(delta, "delta", torch.float32)
+    assert delta.shape[0] == ids.numel() and delta.shape[1] <= tab.stride
+    _check(lib().fps_push_add(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
+                              C.c_longlong(ids.numel()), C.c_void_p(delta.data_ptr()),
+                              int(delta.shape[1]), C.c_float(scale), int(bool(touch)),
+                              C.c_void_p(nan_flag.data_ptr() if nan_flag is not None else None),
+                              sm_count(ids.device.index), _stream()), "push_add")
+    _bump()
+
+
+def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: torch.Tensor) -> None:
+    _req(ids, "ids"); _req(local, "local", torch.float32); _req(score, "score", torch.float32)
+    assert local.shape[0] == ids.numel() == score.numel()
+    _check(lib().fps_pull_dot(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
+                              C.c_longlong(ids.numel()), C.c_void_p(local.data_ptr()),
+                              int(local.shape[1]), C.c_void_p(score.data_ptr()),
+                              sm_count(ids.device.index), _stream()), "pull_dot")
+    _bump()

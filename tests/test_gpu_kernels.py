@@ -1,0 +1,165 @@
+"""Numerics of the hand-written sm_100a kernels vs plain PyTorch fp32 references."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def test_native_library_loaded(dev):
+    from fps_b200.ops import native
+
+    assert native.available(), "libfps_kernels.so must be built in-tree"
+    native.lib()
+    maps = open("/proc/self/maps").read()
+    assert "libfps_kernels.so" in maps
+
+
+@pytest.mark.parametrize("dim", [10, 16, 64, 300])
+def test_init_rows_matches_philox_oracle(dev, dim):
+    from fps_b200.store.sharded_table import ShardedTable
+    from tests.philox_ref import init_rows_ref
+
+    t = ShardedTable(1000, dim, seed=42, init_range=(-0.01, 0.01))
+    ids = t.local_ids().cpu().numpy()
+    ref = init_rows_ref(ids, dim, 42, -0.01, 0.01)
+    got = t.local.cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9)
+    assert (got[:, dim:] == 0).all()
+    t.close()
+
+
+@pytest.mark.parametrize("dim,idt", [(10, torch.int64), (64, torch.int32), (128, torch.int64), (300, torch.int32)])
+def test_pull_push_dot(dev, dim, idt):
+    from fps_b200.store.sharded_table import ShardedTable
+
+    n = 5000
+    t = ShardedTable(n, dim, seed=3, init_range=(-1.0, 1.0), track_touched=True)
+    table0 = t.local[:, :dim].clone()
+    ids = torch.randint(0, n, (20000,), device=dev).to(idt)
+    got = t.pull(ids)
+    torch.testing.assert_close(got, table0[ids.long()], rtol=0, atol=0)
+    delta = torch.randn(ids.numel(), dim, device=dev)
+    t.push(ids, delta)
+    ref = table0.clone().index_add_(0, ids.long(), delta)
+    torch.testing.assert_close(t.local[:, :dim], ref, rtol=1e-5, atol=1e-5)
+    loc = torch.randn(ids.numel(), dim, device=dev)
+    s = t.pull_dot(ids, loc)
+    torch.testing.assert_close(s, (ref[ids.long()] * loc).sum(1), rtol=1e-4, atol=1e-4)
+    # touched bitmap == set of pulled ids
+    dumped_ids, dumped = t.dump_local()
+    assert set(dumped_ids.tolist()) == set(ids.long().unique().tolist())
+    t.check_finite()
+    t.push(ids[:1], torch.full((1, dim), float("nan"), device=dev))
+    with pytest.raises(FloatingPointError):
+        t.check_finite()
+    t.close()
+
+
+def _mf_reference(U, V, users, items, ratings, lr, err_mode):
+    u = U[users]; v = V[items]
+    resid = ratings - (u * v).sum(1)
+    e = torch.sigmoid(resid) if err_mode == 0 else resid
+    g = (lr * e)[:, None]
+    U2 = U.clone().index_add_(0, users, g * v)
+    V2 = V.clone().index_add_(0, items, g * u)
+    return U2, V2, (resid ** 2).sum()
+
+
+@pytest.mark.parametrize("k,idt,err_mode", [(64, torch.int32, 0), (64, torch.int64, 1), (10, torch.int32, 0),
+                                            (16, torch.int32, 1), (128, torch.int64, 0), (300, torch.int32, 0)])
+def test_mf_sgd_fused_matches_reference(dev, k, idt, err_mode):
+    """Unique (user, item) per batch => the async kernel is deterministic and must equal fp32 torch."""
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    nu, ni, b = 6000, 5000, 4000
+    m = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, err_mode=err_mode)
+    U = m.users[:, :k].clone(); V = m.items.local[:, :k].clone()
+    users = torch.randperm(nu, device=dev)[:b]
+    items = torch.randperm(ni, device=dev)[:b]
+    ratings = torch.rand(b, device=dev) * 2
+    m.step(users.to(idt), items.to(idt), ratings)
+    torch.cuda.synchronize()
+    U2, V2, sq = _mf_reference(U, V, users, items, ratings, 0.05, err_mode)
+    torch.testing.assert_close(m.users[:, :k], U2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m.items.local[:, :k], V2, rtol=1e-5, atol=1e-6)
+    s = m.stats.cpu()
+    assert s[1].item() == b
+    assert abs(s[0].item() - sq.item()) / sq.item() < 1e-4
+    m.check_finite()
+    m.close()
+
+
+def test_mf_sgd_fused_duplicates_lose_no_update(dev):
+    """Hogwild with atomics: with lr*e forced constant the sum of deltas is order independent."""
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    k = 64
+    m = DeviceOnlineMF(8, 4, k, range_min=0.1, range_max=0.2, learning_rate=0.0, seed=1, err_mode=1)
+    U = m.users[:, :k].clone(); V = m.items.local[:, :k].clone()
+    users = torch.randint(0, 8, (10000,), device=dev, dtype=torch.int32)
+    items = torch.randint(0, 4, (10000,), device=dev, dtype=torch.int32)
+    m.step(users, items, torch.ones(10000, device=dev))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(m.users[:, :k], U)  # lr = 0 -> nothing moves, nothing corrupt
+    torch.testing.assert_close(m.items.local[:, :k], V)
+    assert m.stats[1].item() == 10000
+    m.close()
+
+
+def test_mf_converges_rmse_gate(dev):
+    """Model-quality gate mirroring PSOfflineMatrixFactorizationTest.scala:55-103 (RMSE <= 0.5)."""
+    from fps_b200.models.mf.device import DeviceOnlineMF, ERR_PLAIN
+
+    g = torch.Generator().manual_seed(47)
+    nu, ni, k = 20, 15, 15
+    users = torch.randint(0, nu, (100,), generator=g, dtype=torch.int32).cuda()
+    items = torch.randint(0, ni, (100,), generator=g, dtype=torch.int32).cuda()
+    ratings = torch.rand(100, generator=g).cuda()
+    m = DeviceOnlineMF(nu, ni, k, range_min=0.0, range_max=1.0 / k ** 0.5, learning_rate=0.05, seed=47,
+                       err_mode=ERR_PLAIN)
+    for _ in range(200):
+        m.step(users, items, ratings)
+    pred = m.predict(users, items)
+    rmse = ((pred - ratings) ** 2).mean().sqrt().item()
+    assert rmse <= 0.5, rmse
+    m.close()
+
+
+def test_mf_negative_sampling_counts(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    m = DeviceOnlineMF(1000, 500, 32, learning_rate=0.01, negative_sample_rate=3, seed=9)
+    V0 = m.items.local.clone()
+    users = torch.randint(0, 1000, (2048,), device=dev, dtype=torch.int32)
+    items = torch.randint(0, 500, (2048,), device=dev, dtype=torch.int32)
+    m.step(users, items, torch.ones(2048, device=dev))
+    torch.cuda.synchronize()
+    assert m.stats[1].item() == 2048 * 4
+    changed = (m.items.local != V0).any(1).sum().item()
+    assert changed > 400  # negatives touch (almost) every item
+    m.check_finite()
+    m.close()
+
+
+def test_fit_stream_end_to_end(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    m = DeviceOnlineMF(5000, 3000, 64, learning_rate=0.01, seed=2)
+    g = torch.Generator().manual_seed(1)
+    batches = []
+    for _ in range(7):
+        batches.append((torch.randint(0, 5000, (4096,), generator=g, dtype=torch.int32).pin_memory(),
+                        torch.randint(0, 3000, (4096,), generator=g, dtype=torch.int32).pin_memory(),
+                        torch.rand(4096, generator=g).pin_memory()))
+    res = list(m.fit_stream(iter(batches)))
+    assert len(res) == 7
+    assert all(c == 4096 for _, c in res)
+    assert all(np.isfinite(s) for s, _ in res)
+    m.close()
