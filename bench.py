@@ -36,8 +36,8 @@ sys.path.insert(0, REPO)
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
-    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--steps", type=int, default=400)
+    p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="fps_b200", choices=["fps_b200", "reference", "nccl"])
     p.add_argument("--users", type=int, default=10_000_000)
     p.add_argument("--items", type=int, default=1_000_000)
@@ -52,7 +52,7 @@ def parse():
 class ClockSampler:
     """Sample SM clocks / throttle reasons with nvidia-smi during the timed region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -64,12 +64,15 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, windows=()):
+        """Summarise samples that fall inside the timed ``windows`` [(t0, t1) wall-clock seconds]."""
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -78,22 +81,27 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]),
+                             [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        inside = [r for r in rows if any(t0 - 0.05 <= r[0] <= t1 + 0.05 for t0, t1 in windows)]
+        window = "timed regions"
+        if not inside:
+            inside, window = rows, "whole run (timed regions shorter than the sampling period)"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None,
+                "sm_max_mhz": max([r[2] for r in inside]) if inside else None,
+                "power_w_max": max([r[3] for r in inside]) if inside else None,
+                "samples": len(inside), "window": window, "reasons": reasons}
 
 
 def main():
@@ -146,12 +154,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-timed --------------------------------------------------------------------------
-    for s in range(a.warmup):
-        model.step(*devb[s % len(devb)])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    windows = []
+    for s in range(a.warmup):
+        model.step(*devb[s % len(devb)])
+    barrier()
+    w0 = time.time()
     launches0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -161,8 +171,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = native.launch_count() - launches0
+    windows.append((w0, time.time()))
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -177,6 +187,7 @@ def main():
     for _ in model.fit_stream(stream(a.warmup)):
         pass
     barrier()
+    w0 = time.time()
     t0 = time.perf_counter()
     e0.record()
     n_res = 0
@@ -186,6 +197,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    windows.append((w0, time.time()))
+    clocks = sampler.stop(windows) if rank == 0 else None
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:

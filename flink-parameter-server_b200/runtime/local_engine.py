@@ -1,0 +1,279 @@
+"""In-process asynchronous engine: workers and PS shards as threads with FIFO inboxes.
+
+This is the host-tier execution backend ("CPU backend" of SURVEY §7.1-2): it runs arbitrary
+Python ``WorkerLogic`` / ``ParameterServerLogic`` callbacks with the reference's semantics --
+
+* the dataflow of ``FlinkParameterServer.transform`` (FPS:340-481): data -> worker ``onRecv``;
+  worker requests -> ``paramPartitioner`` -> PS shard -> receiver -> ``onPullRecv/onPushRecv``;
+  answers -> ``wInPartition`` (worker index, range checked FPS:455-463) -> worker receiver ->
+  ``onPullRecv``; worker outputs ``Left``, PS outputs ``Right``;
+* FIFO per (producer, consumer) pair, which the reference's per-id answer queues rely on
+  (SURVEY §3.2);
+* termination: the reference stops when the feedback edge is idle for ``iterationWaitTime`` ms
+  (FPS:49-52, 480).  Here idleness is *detected* (all sources exhausted, no message in flight,
+  all batching senders flushed) and then has to persist for ``iterationWaitTime`` ms, so finite
+  jobs end promptly while logics with background threads still get their grace period.
+
+It is also the semantic oracle for the device tier's tests.
+"""
+from __future__ import annotations
+
+import copy
+import queue
+import threading
+import time
+from typing import Any, Callable, List, Optional
+
+from ..api import (Left, LooseParameterServerLogic, LooseWorkerLogic, ParameterServer,
+                   ParameterServerClient, Right, RuntimeContext)
+from ..protocol.messages import PullAnswer
+from ..protocol.senders import PSReceiver, PSSender, WorkerReceiver, WorkerSender
+from .stream import DataStream, ResultStream, as_stream
+
+_DATA, _ANSWER, _REQ, _STOP = 0, 1, 2, 3
+
+
+def clone_logic(obj: Any) -> Any:
+    """Per-subtask copy of a logic / sender object (Flink serialises one copy per subtask)."""
+    if hasattr(obj, "fork") and callable(obj.fork):
+        return obj.fork()
+    try:
+        return copy.deepcopy(obj)
+    except Exception:
+        return obj
+
+
+class _Activity:
+    """In-flight accounting for quiescence detection."""
+
+    def __init__(self):
+        self.lock = threading.Lock()
+        self.inflight = 0
+        self.last_event = time.monotonic()
+        self.sources_open = 0
+        self.error: Optional[BaseException] = None
+
+    def add(self, n: int = 1) -> None:
+        with self.lock:
+            self.inflight += n
+            self.last_event = time.monotonic()
+
+    def done(self, n: int = 1) -> None:
+        with self.lock:
+            self.inflight -= n
+            self.last_event = time.monotonic()
+
+    def idle_for(self) -> float:
+        with self.lock:
+            if self.inflight != 0 or self.sources_open != 0:
+                return 0.0
+            return time.monotonic() - self.last_event
+
+
+class MessagingPSClient(ParameterServerClient):
+    """Adapts the client API to the worker sender (FPS:1203-1230); thread safe."""
+
+    def __init__(self, sender: WorkerSender, partitionId: int, emit_to_ps, emit_output):
+        self.sender = sender
+        self.partitionId = partitionId
+        self._emit_to_ps = emit_to_ps
+        self._emit_output = emit_output
+
+    def pull(self, id) -> None:
+        self.sender.onPull(id, self._emit_to_ps, self.partitionId)
+
+    def push(self, id, deltaUpdate) -> None:
+        self.sender.onPush(id, deltaUpdate, self._emit_to_ps, self.partitionId)
+
+    def output(self, out) -> None:
+        self._emit_output(Left(out))
+
+
+class MessagingPS(ParameterServer):
+    """Adapts the server API to the PS sender (FPS:1178-1198)."""
+
+    def __init__(self, sender: PSSender, emit_to_worker, emit_output):
+        self.sender = sender
+        self._emit_to_worker = emit_to_worker
+        self._emit_output = emit_output
+
+    def answerPull(self, id, value, workerPartitionIndex) -> None:
+        self.sender.onPullAnswer(id, value, workerPartitionIndex, self._emit_to_worker)
+
+    def output(self, out) -> None:
+        self._emit_output(Right(out))
+
+
+class LocalEngine:
+    def __init__(self, workerParallelism: int, psParallelism: int, iterationWaitTime: float,
+                 call_worker_open: bool = True):
+        self.wP = int(workerParallelism)
+        self.psP = int(psParallelism)
+        self.wait_s = max(0.0, float(iterationWaitTime) / 1000.0)
+        self.call_worker_open = call_worker_open
+
+    def run(self, trainingData, workerLogic: LooseWorkerLogic, psLogic: LooseParameterServerLogic,
+            paramPartitioner: Callable[[Any], int], wInPartition: Callable[[Any], int],
+            workerReceiver: WorkerReceiver, workerSender: WorkerSender, psReceiver: PSReceiver,
+            psSender: PSSender) -> ResultStream:
+        stream: DataStream = as_stream(trainingData)
+        act = _Activity()
+        results: List[Any] = []
+        res_lock = threading.Lock()
+        w_inbox = [queue.SimpleQueue() for _ in range(self.wP)]
+        ps_inbox = [queue.SimpleQueue() for _ in range(self.psP)]
+
+        def emit_output(x) -> None:
+            with res_lock:
+                results.append(x)
+
+        def emit_to_ps(msg) -> None:
+            dest = int(paramPartitioner(msg)) % self.psP
+            act.add()
+            ps_inbox[dest].put((_REQ, msg))
+
+        def emit_to_worker(msg) -> None:
+            dest = int(wInPartition(msg))
+            if not 0 <= dest < self.wP:
+                raise RuntimeError("Pull answer key should be the partition ID itself!")
+            act.add()
+            w_inbox[dest].put((_ANSWER, msg))
+
+        # per-subtask copies, like Flink's serialised operator instances
+        w_logic = [clone_logic(workerLogic) for _ in range(self.wP)]
+        w_send = [clone_logic(workerSender) for _ in range(self.wP)]
+        w_recv = [clone_logic(workerReceiver) for _ in range(self.wP)]
+        p_logic = [clone_logic(psLogic) for _ in range(self.psP)]
+        p_send = [clone_logic(psSender) for _ in range(self.psP)]
+        p_recv = [clone_logic(psReceiver) for _ in range(self.psP)]
+        for s in w_send:
+            if hasattr(s, "bind_partitioner"):
+                s.bind_partitioner(lambda m: int(paramPartitioner(m)) % self.psP)
+        for s in p_send:
+            if hasattr(s, "bind_partitioner"):
+                s.bind_partitioner(lambda m: int(wInPartition(m)))
+        clients = [MessagingPSClient(w_send[i], i, emit_to_ps, emit_output) for i in range(self.wP)]
+        servers = [MessagingPS(p_send[j], emit_to_worker, emit_output) for j in range(self.psP)]
+
+        def fail(e: BaseException) -> None:
+            with act.lock:
+                if act.error is None:
+                    act.error = e
+
+        def worker_loop(i: int) -> None:
+            logic, recv, client = w_logic[i], w_recv[i], clients[i]
+            try:
+                if self.call_worker_open:
+                    logic.open()
+                while True:
+                    kind, payload = w_inbox[i].get()
+                    if kind == _STOP:
+                        break
+                    try:
+                        if kind == _DATA:
+                            logic.onRecv(payload, client)
+                        else:
+                            recv.onPullAnswerRecv(
+                                payload, lambda a: logic.onPullRecv(a.paramId, a.param, client))
+                    finally:
+                        act.done()
+            except BaseException as e:  # noqa: BLE001
+                fail(e)
+
+        def ps_loop(j: int) -> None:
+            logic, recv, server = p_logic[j], p_recv[j], servers[j]
+            try:
+                logic.open({}, RuntimeContext(j, self.psP))
+                while True:
+                    kind, payload = ps_inbox[j].get()
+                    if kind == _STOP:
+                        break
+                    try:
+                        recv.onWorkerMsg(payload,
+                                         lambda id, widx: logic.onPullRecv(id, widx, server),
+                                         lambda id, delta: logic.onPushRecv(id, delta, server))
+                    finally:
+                        act.done()
+            except BaseException as e:  # noqa: BLE001
+                fail(e)
+
+        # ---- sources ---------------------------------------------------------------------
+        groups = {}
+        for s in stream.sources:
+            if s.group is not None:
+                groups[s.group] = groups.get(s.group, 0) + 1
+        group_lock = threading.Lock()
+        act.sources_open = len(stream.sources)
+
+        def feed(src) -> None:
+            counter = [src.index]
+            try:
+                for rec in src.make_iter():
+                    if act.error is not None:
+                        break
+                    for t in src.routing.targets(rec, self.wP, src.index, counter):
+                        act.add()
+                        w_inbox[t].put((_DATA, rec))
+                if src.group is not None:
+                    with group_lock:
+                        groups[src.group] -= 1
+                        last = groups[src.group] == 0
+                    if last:
+                        marker = stream.eof_markers[src.group]
+                        for t in range(self.wP):
+                            act.add()
+                            w_inbox[t].put((_DATA, marker()))
+            except BaseException as e:  # noqa: BLE001
+                fail(e)
+            finally:
+                with act.lock:
+                    act.sources_open -= 1
+                    act.last_event = time.monotonic()
+
+        threads = [threading.Thread(target=worker_loop, args=(i,), daemon=True, name=f"fps-worker-{i}")
+                   for i in range(self.wP)]
+        threads += [threading.Thread(target=ps_loop, args=(j,), daemon=True, name=f"fps-ps-{j}")
+                    for j in range(self.psP)]
+        feeders = [threading.Thread(target=feed, args=(s,), daemon=True, name=f"fps-src-{k}")
+                   for k, s in enumerate(stream.sources)]
+        for t in threads + feeders:
+            t.start()
+
+        # ---- termination: detected idleness that persists for iterationWaitTime ----------------
+        flushed_idle = False
+        while True:
+            if act.error is not None:
+                break
+            idle = act.idle_for()
+            if idle > 0.0 or (act.inflight == 0 and act.sources_open == 0):
+                if not flushed_idle:
+                    # flush batching senders; they may produce new traffic
+                    for i, s in enumerate(w_send):
+                        s.flush(emit_to_ps)
+                    for j, s in enumerate(p_send):
+                        s.flush(emit_to_worker)
+                    flushed_idle = True
+                    continue
+                if idle >= self.wait_s:
+                    break
+            else:
+                flushed_idle = False
+            time.sleep(0.0005 if self.wait_s < 0.05 else 0.002)
+
+        for q in w_inbox + ps_inbox:
+            q.put((_STOP, None))
+        for t in threads:
+            t.join(timeout=10.0)
+        if act.error is not None:
+            for s in w_send + p_send:
+                s.close()
+            raise act.error
+        # close hooks (worker close, then PS close which may dump the model)
+        for lg in w_logic:
+            lg.close()
+        for j, lg in enumerate(p_logic):
+            lg.close(servers[j])
+        for s in w_send + p_send:
+            s.close()
+        self.worker_logics, self.ps_logics = w_logic, p_logic
+        return ResultStream(results)

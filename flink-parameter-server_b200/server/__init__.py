@@ -1,0 +1,2 @@
+from .logics import (LockPSLogicA, LockPSLogicB, LooseSimplePSLogic, LooseSimplePSLogicWithClose,
+                     RangePSLogicWithClose, SimplePSLogic, SimplePSLogicWithClose)
