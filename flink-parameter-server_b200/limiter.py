@@ -77,7 +77,14 @@ class _PullLimiter(LooseWorkerLogic):
     def updateModel(self, id, param) -> None:
         self.inner.updateModel(id, param)
 
+    def fork(self):
+        from .runtime.local_engine import clone_logic
+
+        return _PullLimiter(clone_logic(self.inner), self.pullLimit)
+
     def __getattr__(self, name):  # expose the wrapped logic's extra attributes
+        if name in ("inner", "fork"):
+            raise AttributeError(name)
         return getattr(self.inner, name)
 
 
@@ -141,7 +148,14 @@ class _BlockingPullLimiter(LooseWorkerLogic):
     def updateModel(self, id, param) -> None:
         self.inner.updateModel(id, param)
 
+    def fork(self):
+        from .runtime.local_engine import clone_logic
+
+        return _BlockingPullLimiter(clone_logic(self.inner), self.pullLimit)
+
     def __getattr__(self, name):
+        if name in ("inner", "fork"):
+            raise AttributeError(name)
         return getattr(self.inner, name)
 
 

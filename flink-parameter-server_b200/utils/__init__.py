@@ -1,0 +1,3 @@
+from .eof import EOF, EOFHandler, flatMapWithEOF, with_eof
+from .input_source import EventWithTimestamp, InputSource
+from .sleep_blocker import block
