@@ -74,6 +74,21 @@ class Right:
 Either = (Left, Right)
 
 
+class CtorFork:
+    """Mixin: remember constructor arguments so the engine can build one fresh instance per
+    parallel subtask with ``fork()`` (the analogue of Flink shipping a serialised copy of the logic
+    to every subtask).  Use it for logics that own locks, threads or RNGs (not deep-copyable)."""
+
+    def __new__(cls, *args, **kwargs):
+        obj = super().__new__(cls)
+        obj._ctor_args = (args, kwargs)
+        return obj
+
+    def fork(self):
+        args, kwargs = self._ctor_args
+        return type(self)(*args, **kwargs)
+
+
 # ------------------------------------------------------------------------------------------
 # worker side
 # ------------------------------------------------------------------------------------------

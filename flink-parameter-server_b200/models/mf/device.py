@@ -36,7 +36,8 @@ class DeviceOnlineMF:
                  range_min: float = -0.01, range_max: float = 0.01, learning_rate: float = 0.01,
                  negative_sample_rate: int = 0, pull_limit: int = DEFAULT_DEVICE_PULL_LIMIT,
                  group=None, seed: int = 0, err_mode: int = ERR_SIGMOID,
-                 device: Optional[int] = None, track_touched: bool = False):
+                 device: Optional[int] = None, track_touched: bool = False,
+                 kernel: Optional[str] = None):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -50,6 +51,7 @@ class DeviceOnlineMF:
         self.err_mode = int(err_mode)
         self.seed = int(seed)
         self.step_no = 0
+        self.kernel = kernel
         with torch.cuda.device(self.device):
             # parameter server: item vectors, sharded item % psParallelism
             self.items = ShardedTable(num_items, num_factors, partition="hash", group=group,
@@ -73,7 +75,7 @@ class DeviceOnlineMF:
                             self.lr, err_mode=self.err_mode, neg_rate=self.neg,
                             num_items=self.num_items, seed=self.seed, step=self.step_no,
                             stats=self.stats, nan_flag=self.nan_flag,
-                            max_inflight_rows=self.pull_limit)
+                            max_inflight_rows=self.pull_limit, kernel=self.kernel)
         self.step_no += 1
 
     def fit_stream(self, host_batches: Iterable[Sequence[torch.Tensor]],

@@ -1,0 +1,118 @@
+"""Offline (multi-epoch) SGD matrix factorisation -- ``psOfflineMF``.
+
+Reference: M/matrix/factorization/PSOfflineMatrixFactorization.scala:46-107 and
+workers/PSOfflineMatrixFactorizationWorker.scala:28-151: buffer all ratings (+negatives) until the
+EOF of the finite input, then a background thread issues the pulls for ``iterations`` epochs while
+the operator thread handles the answers.  ``shuffle=True`` actually reshuffles between epochs (the
+reference discards the result of ``Random.shuffle``).
+"""
+from __future__ import annotations
+
+import random
+import threading
+from collections import deque
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from ...api import CtorFork, WorkerLogic
+from ...limiter import addPullLimiter
+from ...runtime.stream import as_stream
+from ...runtime.transform import transform
+from ...utils.eof import EOF, with_eof
+from .common import Rating, RangedRandomFactorInitializerDescriptor, SGDUpdater, vectorSum
+from .online import NegativeSampler
+
+
+class PSOfflineMatrixFactorizationWorker(CtorFork, WorkerLogic):
+    def __init__(self, numFactors, rangeMin, rangeMax, learningRate, negativeSampleRate, userMemory,
+                 iterations, seed: Optional[int] = None, plain_residual: bool = False,
+                 shuffle: bool = False):
+        self.factorInitDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax, seed)
+        self._init = None
+        self.factorUpdate = SGDUpdater(learningRate, plain_residual)
+        self.iterations = iterations
+        self.shuffle = shuffle
+        self.rbs: List[List[Rating]] = []
+        self.userVectors: Dict[int, np.ndarray] = {}
+        self.ratingBuffer: Dict[int, deque] = {}
+        self.sampler = NegativeSampler(userMemory, negativeSampleRate, seed)
+        self.workerThread: Optional[threading.Thread] = None
+        self._lock = threading.Lock()
+        self._rnd = random.Random(seed)
+
+    def onRecv(self, value, ps):
+        if isinstance(value, EOF):
+            def run():
+                for _ in range(self.iterations):
+                    if self.shuffle:
+                        self._rnd.shuffle(self.rbs)
+                    for rs in self.rbs:
+                        for rating in rs:
+                            with self._lock:
+                                self.ratingBuffer.setdefault(rating.item, deque()).append(
+                                    (rating.user, rating.rating))
+                            ps.pull(rating.item)
+
+            self.workerThread = threading.Thread(target=run, daemon=True, name="fps-offline-mf")
+            self.workerThread.start()
+            return
+        if self.workerThread is not None:
+            raise RuntimeError("Should not have started worker thread while waiting for further elements.")
+        rating: Rating = value
+        self.sampler.register_item(rating.item)
+        seen = self.sampler.observe(rating.user, rating.item)
+        rs = [Rating(rating.user, neg, 0.0) for neg in self.sampler.sample(seen)]
+        rs.append(rating)
+        self.rbs.append(rs)
+
+    def onPullRecv(self, item, itemVec, ps):
+        with self._lock:
+            user, rating = self.ratingBuffer[item].popleft()
+        userVec = self.userVectors.get(user)
+        if userVec is None:
+            if self._init is None:
+                self._init = self.factorInitDesc.open()
+            userVec = self._init.nextFactor(user)
+        du, dv = self.factorUpdate.delta(rating, userVec, itemVec)
+        self.userVectors[user] = vectorSum(userVec, du)
+        ps.output((user, self.userVectors[user]))
+        ps.push(item, dv)
+
+    def close(self):
+        if self.workerThread is not None:
+            self.workerThread.join(timeout=30)
+
+
+def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: float = 0.01,
+                learningRate: float = 0.01, negativeSampleRate: int = 0, userMemory: int = 128,
+                iterations: int = 10, pullLimit: int = 1600, workerParallelism: int = 1,
+                psParallelism: int = 1, iterationWaitTime: float = 10000, seed: Optional[int] = None,
+                plain_residual: bool = False, shuffle: bool = False, backend: str = "local",
+                **device_kw):
+    if backend == "device":
+        from .device_api import ps_offline_mf_device
+
+        return ps_offline_mf_device(src, numFactors=numFactors, rangeMin=rangeMin, rangeMax=rangeMax,
+                                    learningRate=learningRate, negativeSampleRate=negativeSampleRate,
+                                    iterations=iterations, pullLimit=pullLimit, seed=seed or 0,
+                                    plain_residual=plain_residual, **device_kw)
+    initDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax,
+                                                       None if seed is None else seed + 1)
+    holder = {}
+
+    def paramInit(i):
+        if "f" not in holder:
+            holder["f"] = initDesc.open()
+        return holder["f"].nextFactor(i)
+
+    ratings = with_eof(src, lambda key, n: key % n, lambda r: r.user)
+    worker = addPullLimiter(
+        PSOfflineMatrixFactorizationWorker(numFactors, rangeMin, rangeMax, learningRate,
+                                           negativeSampleRate, userMemory, iterations, seed,
+                                           plain_residual, shuffle), pullLimit)
+    return transform(ratings, worker, paramInit, vectorSum, workerParallelism, psParallelism,
+                     iterationWaitTime)
+
+
+ps_offline_mf = psOfflineMF

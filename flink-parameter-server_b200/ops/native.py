@@ -213,8 +213,12 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  user_table: torch.Tensor, user_div: int, item_tab: ShardTableC, lr: float,
                  err_mode: int = 0, neg_rate: int = 0, num_items: int = 0, seed: int = 0,
                  step: int = 0, stats: Optional[torch.Tensor] = None,
-                 nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0) -> None:
-    """Fused pull + SGD + push (K1+K3+K2).  See csrc/fps_core.cu."""
+                 nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
+                 kernel: Optional[str] = None) -> None:
+    """Fused pull + SGD + push (K1+K3+K2).
+
+    ``kernel="tma"`` (default): warp-specialised TMA/mbarrier pipeline (csrc/fps_mf_tma.cu);
+    ``kernel="reg"``: register-staged variant (csrc/fps_core.cu)."""
     _req(users, "users"); _req(items, "items"); _req(ratings, "ratings", torch.float32)
     _req(user_table, "user_table", torch.float32)
     if users.dtype != items.dtype:
@@ -230,6 +234,14 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.stats = stats.data_ptr() if stats is not None else None
     a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
     a.item_tab = item_tab
+    variant = kernel or os.environ.get("FPS_MF_KERNEL", "tma")
+    if variant == "tma":
+        code = lib().fps_mf_sgd_tma(C.byref(a), _id_bytes(users), int(max_inflight_rows),
+                                    sm_count(users.device.index), _stream())
+        if code != -1002:  # -1002: rows too large for the smem ring -> register-staged kernel
+            _check(code, "mf_sgd_tma")
+            _bump()
+            return
     _check(lib().fps_mf_sgd_fused(C.byref(a), _id_bytes(users), int(max_inflight_rows),
                                   sm_count(users.device.index), _stream()), "mf_sgd_fused")
     _bump()

@@ -39,8 +39,10 @@ def clone_logic(obj: Any) -> Any:
         return obj.fork()
     try:
         return copy.deepcopy(obj)
-    except Exception:
-        return obj
+    except Exception as e:
+        raise TypeError(
+            f"{type(obj).__name__} cannot be copied per subtask ({e}); give it a fork() method "
+            "(e.g. inherit fps_b200.api.CtorFork)") from e
 
 
 class _Activity:

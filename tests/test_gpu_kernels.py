@@ -72,14 +72,19 @@ def _mf_reference(U, V, users, items, ratings, lr, err_mode):
     return U2, V2, (resid ** 2).sum()
 
 
+@pytest.mark.parametrize("kernel", ["tma", "reg"])
 @pytest.mark.parametrize("k,idt,err_mode", [(64, torch.int32, 0), (64, torch.int64, 1), (10, torch.int32, 0),
-                                            (16, torch.int32, 1), (128, torch.int64, 0), (300, torch.int32, 0)])
-def test_mf_sgd_fused_matches_reference(dev, k, idt, err_mode):
+                                            (16, torch.int32, 1), (128, torch.int64, 0), (300, torch.int32, 0),
+                                            (4, torch.int32, 1), (1000, torch.int32, 0)])
+def test_mf_sgd_fused_matches_reference(dev, k, idt, err_mode, kernel):
     """Unique (user, item) per batch => the async kernel is deterministic and must equal fp32 torch."""
     from fps_b200.models.mf.device import DeviceOnlineMF
 
     nu, ni, b = 6000, 5000, 4000
-    m = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, err_mode=err_mode)
+    m = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, err_mode=err_mode,
+                       kernel=kernel)
+    if k >= 1000:
+        m.items.local.mul_(0.05); m.users.mul_(0.05)   # keep |u.v| moderate for the fp32 comparison
     U = m.users[:, :k].clone(); V = m.items.local[:, :k].clone()
     users = torch.randperm(nu, device=dev)[:b]
     items = torch.randperm(ni, device=dev)[:b]
@@ -96,12 +101,14 @@ def test_mf_sgd_fused_matches_reference(dev, k, idt, err_mode):
     m.close()
 
 
-def test_mf_sgd_fused_duplicates_lose_no_update(dev):
-    """Hogwild with atomics: with lr*e forced constant the sum of deltas is order independent."""
+@pytest.mark.parametrize("kernel", ["tma", "reg"])
+def test_mf_sgd_fused_duplicates_lose_no_update(dev, kernel):
+    """Hot rows hammered by every lane-group: nothing corrupt, every update counted."""
     from fps_b200.models.mf.device import DeviceOnlineMF
 
     k = 64
-    m = DeviceOnlineMF(8, 4, k, range_min=0.1, range_max=0.2, learning_rate=0.0, seed=1, err_mode=1)
+    m = DeviceOnlineMF(8, 4, k, range_min=0.1, range_max=0.2, learning_rate=0.0, seed=1, err_mode=1,
+                       kernel=kernel)
     U = m.users[:, :k].clone(); V = m.items.local[:, :k].clone()
     users = torch.randint(0, 8, (10000,), device=dev, dtype=torch.int32)
     items = torch.randint(0, 4, (10000,), device=dev, dtype=torch.int32)
@@ -132,10 +139,11 @@ def test_mf_converges_rmse_gate(dev):
     m.close()
 
 
-def test_mf_negative_sampling_counts(dev):
+@pytest.mark.parametrize("kernel", ["tma", "reg"])
+def test_mf_negative_sampling_counts(dev, kernel):
     from fps_b200.models.mf.device import DeviceOnlineMF
 
-    m = DeviceOnlineMF(1000, 500, 32, learning_rate=0.01, negative_sample_rate=3, seed=9)
+    m = DeviceOnlineMF(1000, 500, 32, learning_rate=0.01, negative_sample_rate=3, seed=9, kernel=kernel)
     V0 = m.items.local.clone()
     users = torch.randint(0, 1000, (2048,), device=dev, dtype=torch.int32)
     items = torch.randint(0, 500, (2048,), device=dev, dtype=torch.int32)
