@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--lr", type=float, default=0.01)
     p.add_argument("--pull-limit", type=int, default=0, help="0 = hardware max rows in flight")
     p.add_argument("--host-buffers", type=int, default=6)
+    p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
+                   help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()
 
 
@@ -134,7 +136,7 @@ def main():
     else:
         Model = DeviceOnlineMF
     model = Model(a.users, a.items, a.factors, learning_rate=a.lr, pull_limit=a.pull_limit,
-                  seed=1234, err_mode=ERR_SIGMOID)
+                  seed=1234, err_mode=ERR_SIGMOID, kernel=a.kernel)
 
     # ---- synthetic ratings: users owned by this worker (user % W == rank), uniform items -------
     g = torch.Generator().manual_seed(1000 + rank)
@@ -217,7 +219,7 @@ def main():
             "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "impl": a.impl,
+            "impl": a.impl, "kernel": a.kernel or os.environ.get("FPS_MF_KERNEL", "tma"),
             "config": {"model": "online SGD MF 10Mx1M k=64 (psOnlineMF)", "users": a.users,
                        "items": a.items, "factors": a.factors,
                        "global_batch": a.batch * world, "per_gpu_batch": a.batch,

@@ -123,6 +123,13 @@ class _PerDestinationBatcher:
         """Bind ``message -> destination`` so batches become per-destination (K11)."""
         self._partition = fn
 
+    def fork(self):
+        """Fresh sender with the same triggers (one per parallel subtask)."""
+        new = object.__new__(type(self))
+        _PerDestinationBatcher.__init__(new, self._proto.condition,
+                                        [c.fork() for c in self._proto.combinables])
+        return new
+
     def _logic_for(self, single_msg) -> CombinationLogic:
         if self._partition is None:
             return self._proto
