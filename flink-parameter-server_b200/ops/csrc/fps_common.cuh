@@ -22,6 +22,8 @@ struct ShardTable {
   int dim;     // logical row length in floats
   int stride;  // physical row stride in floats (multiple of 4, zero padded)
   int mode;    // FpsPartition
+  int shard_shift;  // log2(num_shards) if it is a power of two, else -1 (fast hash locate)
+  int pad_;
 };
 
 // id -> (owner shard, slot).  Hash mode mirrors `abs(id.hashCode) % psParallelism`
@@ -37,6 +39,26 @@ __device__ __forceinline__ void fps_locate(const ShardTable& t, long long id, in
     if (owner >= t.num_shards) owner = t.num_shards - 1;
     slot = id - (long long)owner * t.div;
   }
+}
+
+// 32-bit fast path: ids known to fit in an int (IdT == int); shift/mask when G is a power of two.
+__device__ __forceinline__ float* fps_row32(const ShardTable& t, int id) {
+  if (t.mode == FPS_PART_HASH) {
+    const unsigned a = (unsigned)(id < 0 ? -id : id);
+    unsigned owner, slot;
+    if (t.shard_shift >= 0) {
+      owner = a & ((1u << t.shard_shift) - 1u);
+      slot = a >> t.shard_shift;
+    } else {
+      slot = a / (unsigned)t.num_shards;
+      owner = a - slot * (unsigned)t.num_shards;
+    }
+    return t.base[owner] + (size_t)slot * (size_t)t.stride;
+  }
+  unsigned owner = (unsigned)id / (unsigned)t.div;
+  if (owner >= (unsigned)t.num_shards) owner = t.num_shards - 1;
+  const unsigned slot = (unsigned)id - owner * (unsigned)t.div;
+  return t.base[owner] + (size_t)slot * (size_t)t.stride;
 }
 
 __device__ __forceinline__ float* fps_row(const ShardTable& t, long long id) {
@@ -56,6 +78,19 @@ __device__ __forceinline__ void fps_touch(const ShardTable& t, long long id) {
                  "r"(1u << (slot & 31))
                  : "memory");
   }
+}
+
+template <typename IdT>
+__device__ __forceinline__ float* fps_row_t(const ShardTable& t, IdT id) {
+  if (sizeof(IdT) == 4) return fps_row32(t, (int)id);
+  return fps_row(t, (long long)id);
+}
+// worker-local slot of a user: user / workerParallelism (32-bit / shift fast paths)
+template <typename IdT>
+__device__ __forceinline__ size_t fps_user_slot(IdT user, int user_div, int user_shift) {
+  if (user_shift >= 0) return (size_t)((unsigned long long)user >> user_shift);
+  if (sizeof(IdT) == 4) return (size_t)((unsigned)user / (unsigned)user_div);
+  return (size_t)((long long)user / user_div);
 }
 
 // ---- 16-byte peer-capable memory ops --------------------------------------------------

@@ -77,6 +77,7 @@ struct MfArgs {
   unsigned long long step;    // negative-sample stream counter (micro-batch number)
   float* user_table;          // worker-local [n_local_users, stride]
   int user_div;               // workerParallelism: local slot = user / user_div
+  int user_shift;             // log2(user_div) if power of two, else -1
   float lr;
   int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual
   float* stats;               // [0] += sum (r-u.v)^2, [1] += #updates
@@ -84,15 +85,16 @@ struct MfArgs {
   ShardTable item_tab;
 };
 
-template <typename IdT, int LPR, int VPL, int R>
-__global__ void __launch_bounds__(256)
+template <typename IdT, int LPR, int VPL, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
   const int lane = threadIdx.x & (LPR - 1);
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
   const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
   const int per_pos = 1 + a.neg_rate;
   const long long n_eff = a.n_pos * per_pos;
-  const int nvec = a.item_tab.stride >> 2;
+  const int stride = a.item_tab.stride;
+  const int nvec = stride >> 2;
   const IdT* __restrict__ users = reinterpret_cast<const IdT*>(a.users);
   const IdT* __restrict__ items = reinterpret_cast<const IdT*>(a.items);
   float sq_acc = 0.f, cnt_acc = 0.f;
@@ -114,11 +116,11 @@ __global__ void __launch_bounds__(256)
         pos = idx / per_pos;
         j = (int)(idx - pos * per_pos);
       }
-      long long user = 0, item = 0;
+      IdT user = 0, item = 0;
       rt[r] = 0.f;
       if (ok[r]) {
-        user = (long long)users[pos];
-        item = (long long)items[pos];
+        user = users[pos];
+        item = items[pos];
         if (j == 0) {
           rt[r] = a.ratings[pos];
         } else {
@@ -128,12 +130,12 @@ __global__ void __launch_bounds__(256)
                                  (uint32_t)(a.seed >> 32));
           unsigned long long h = ((unsigned long long)s.x << 32) | s.y;
           long long neg = (long long)(h % (unsigned long long)a.num_items);
-          if (neg == item) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
-          item = neg;
+          if (neg == (long long)item) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
+          item = (IdT)neg;
         }
       }
-      up[r] = a.user_table + (user / a.user_div) * (long long)a.item_tab.stride;
-      vp[r] = fps_row(a.item_tab, item);
+      up[r] = a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
+      vp[r] = fps_row_t<IdT>(a.item_tab, item);
 #pragma unroll
       for (int c = 0; c < VPL; ++c) {
         const int q = lane + c * LPR;
@@ -189,13 +191,13 @@ __global__ void __launch_bounds__(256)
   if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
 }
 
-template <typename IdT, int LPR, int VPL, int R>
+template <typename IdT, int LPR, int VPL, int R, int MINB>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
   const int groups_per_block = threads / LPR;
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R>,
-                                                threads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB>, threads, 0);
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
@@ -208,23 +210,34 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
   if (need < 1) need = 1;
   if (blocks > need) blocks = need;
-  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R><<<(int)blocks, threads, 0, stream>>>(a);
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB><<<(int)blocks, threads, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
+
+static int g_mf_reg_variant = 0;  // tuning knob: (rows in flight per lane-group, min blocks/SM)
+extern "C" void fps_set_mf_reg_variant(int v) { g_mf_reg_variant = v; }
 
 template <typename IdT>
 static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
   const int nvec = a.item_tab.stride >> 2;
-  if (nvec <= 1) return launch_mf<IdT, 1, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 2) return launch_mf<IdT, 2, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 4) return launch_mf<IdT, 4, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 8) return launch_mf<IdT, 8, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 16) return launch_mf<IdT, 16, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 32) return launch_mf<IdT, 32, 1, 4>(a, max_inflight, num_sms, s);
-  if (nvec <= 64) return launch_mf<IdT, 32, 2, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 96) return launch_mf<IdT, 32, 3, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 128) return launch_mf<IdT, 32, 4, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 256) return launch_mf<IdT, 32, 8, 1>(a, max_inflight, num_sms, s);
+  if (nvec <= 1) return launch_mf<IdT, 1, 1, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 2) return launch_mf<IdT, 2, 1, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 4) return launch_mf<IdT, 4, 1, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 8) return launch_mf<IdT, 8, 1, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 16) {
+    switch (g_mf_reg_variant) {
+      case 1: return launch_mf<IdT, 16, 1, 4, 3>(a, max_inflight, num_sms, s);
+      case 2: return launch_mf<IdT, 16, 1, 8, 1>(a, max_inflight, num_sms, s);
+      case 3: return launch_mf<IdT, 16, 1, 2, 4>(a, max_inflight, num_sms, s);
+      case 4: return launch_mf<IdT, 16, 1, 6, 2>(a, max_inflight, num_sms, s);
+      default: return launch_mf<IdT, 16, 1, 4, 2>(a, max_inflight, num_sms, s);
+    }
+  }
+  if (nvec <= 32) return launch_mf<IdT, 32, 1, 4, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 64) return launch_mf<IdT, 32, 2, 2, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 96) return launch_mf<IdT, 32, 3, 2, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 128) return launch_mf<IdT, 32, 4, 2, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 256) return launch_mf<IdT, 32, 8, 1, 2>(a, max_inflight, num_sms, s);
   return -1000;  // dim > 1024 not supported by the fused MF kernel
 }
 
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(256)
   const int nvec = t.stride >> 2;
   for (long long i = group; i < n; i += n_groups) {
     const long long id = (long long)ids[i];
-    const float* src = fps_row(t, id);
+    const float* src = fps_row_t<IdT>(t, ids[i]);
     if (touch && lane == 0) fps_touch(t, id);
     for (int q = lane; q < nvec; q += LPR) {
       float4 v = fps_ld_row4(src + 4 * q);
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(256)
   bool bad = false;
   for (long long i = group; i < n; i += n_groups) {
     const long long id = (long long)ids[i];
-    float* dst = fps_row(t, id);
+    float* dst = fps_row_t<IdT>(t, ids[i]);
     if (touch && lane == 0) fps_touch(t, id);
     for (int q = lane; q < nvec; q += LPR) {
       const float* d = delta + i * (long long)delta_stride + 4 * q;
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(256)
   for (long long i = group; i < n_round; i += n_groups) {
     float d = 0.f;
     if (i < n) {
-      const float* src = fps_row(t, (long long)ids[i]);
+      const float* src = fps_row_t<IdT>(t, ids[i]);
       for (int q = lane; q < nvec; q += LPR) {
         float4 v = fps_ld_row4(src + 4 * q);
         const float* l = local + i * (long long)local_stride + 4 * q;

@@ -29,6 +29,7 @@ struct MfArgs {  // must match fps_core.cu
   unsigned long long step;
   float* user_table;
   int user_div;
+  int user_shift;
   float lr;
   int err_mode;
   float* stats;
@@ -37,8 +38,9 @@ struct MfArgs {  // must match fps_core.cu
 };
 
 #define TILE_ROWS 32
+#define N_PRODUCER_WARPS 2
 #define N_CONSUMER_WARPS 8
-#define TMA_THREADS (32 * (1 + N_CONSUMER_WARPS))
+#define TMA_THREADS (32 * (N_PRODUCER_WARPS + N_CONSUMER_WARPS))
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -113,22 +115,24 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   const long long n_eff = a.n_pos * per_pos;
   const long long n_tiles = (n_eff + TILE_ROWS - 1) / TILE_ROWS;
 
-  if (warp == 0) {
-    // ============================== PRODUCER (TMA issue) ==============================
+  if (warp < N_PRODUCER_WARPS) {
+    // ============================== PRODUCERS (TMA issue) ==============================
+    // CTA-local tile sequence k = 0,1,2,... maps to global tile t = blockIdx.x + k*gridDim.x and to
+    // stage k % n_stages; producer warp pw owns the tiles with k % N_PRODUCER_WARPS == pw
+    // (n_stages is a multiple of N_PRODUCER_WARPS, so each producer owns a fixed set of stages).
     const IdT* __restrict__ users = reinterpret_cast<const IdT*>(a.users);
     const IdT* __restrict__ items = reinterpret_cast<const IdT*>(a.items);
-    int stage = 0;
-    uint32_t phase = 0;
     constexpr int PF = 4;  // tiles whose ids are fetched together (hides the id-load latency)
-    for (long long t0 = blockIdx.x; t0 < n_tiles; t0 += (long long)gridDim.x * PF) {
-      long long user[PF], item[PF];
+    for (long long k0 = warp;; k0 += (long long)N_PRODUCER_WARPS * PF) {
+      if (blockIdx.x + k0 * gridDim.x >= n_tiles) break;
+      IdT user[PF], item[PF];
       float rt[PF];
       bool ok[PF];
       int jj[PF];
       long long pp[PF];
 #pragma unroll
       for (int p = 0; p < PF; ++p) {
-        const long long t = t0 + (long long)p * gridDim.x;
+        const long long t = blockIdx.x + (k0 + (long long)p * N_PRODUCER_WARPS) * gridDim.x;
         const long long idx = t * TILE_ROWS + lane;
         ok[p] = (t < n_tiles) && (idx < n_eff);
         user[p] = 0; item[p] = 0; rt[p] = 0.f; jj[p] = 0; pp[p] = 0;
@@ -139,16 +143,19 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
             pos = idx / per_pos;
             j = (int)(idx - pos * per_pos);
           }
-          user[p] = (long long)users[pos];
-          item[p] = (long long)items[pos];
+          user[p] = users[pos];
+          item[p] = items[pos];
           if (j == 0) rt[p] = a.ratings[pos];
           jj[p] = j; pp[p] = pos;
         }
       }
 #pragma unroll
       for (int p = 0; p < PF; ++p) {
-        const long long t = t0 + (long long)p * gridDim.x;
+        const long long k = k0 + (long long)p * N_PRODUCER_WARPS;
+        const long long t = blockIdx.x + k * gridDim.x;
         if (t >= n_tiles) break;
+        const int stage = (int)(k % n_stages);
+        const uint32_t phase = (uint32_t)((k / n_stages) & 1);
         if (ok[p] && jj[p] != 0) {  // K5: device-side negative sample
           const long long pos = pp[p];
           Philox4 s = fps_philox((uint32_t)pos, (uint32_t)((unsigned long long)pos >> 32),
@@ -156,11 +163,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
                                  (uint32_t)(a.seed >> 32));
           unsigned long long h = ((unsigned long long)s.x << 32) | s.y;
           long long neg = (long long)(h % (unsigned long long)a.num_items);
-          if (neg == item[p]) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
-          item[p] = neg;
+          if (neg == (long long)item[p]) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
+          item[p] = (IdT)neg;
         }
-        float* up = a.user_table + (user[p] / a.user_div) * (long long)stride;
-        float* vp = fps_row(a.item_tab, item[p]);
+        float* up = a.user_table + fps_user_slot<IdT>(user[p], a.user_div, a.user_shift) * (size_t)stride;
+        float* vp = fps_row_t<IdT>(a.item_tab, item[p]);
         mbar_wait(&empty[stage], phase ^ 1u);  // slot free (credit available)
         RowMeta m;
         m.up = up; m.vp = vp; m.rating = rt[p]; m.valid = ok[p] ? 1 : 0;
@@ -176,12 +183,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           tma_bulk_g2s(sv, vp, row_bytes, &full[stage]);  // the PULL (peer HBM over NVLink or local)
           tma_bulk_g2s(su, up, row_bytes, &full[stage]);
         }
-        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ============================== CONSUMERS (SGD + PUSH) ==============================
-    const int cw = warp - 1;
+    const int cw = warp - N_PRODUCER_WARPS;
     constexpr int ROWS_PER_PASS = 32 / LPR;
     const int sub = lane / LPR;
     const int l = lane & (LPR - 1);
@@ -251,6 +257,7 @@ static int launch_tma(const MfArgs& a, int max_inflight_rows, int num_sms, cudaS
     if (cap < 2) cap = 2;
     if (stages > cap) stages = cap;
   }
+  stages -= stages % N_PRODUCER_WARPS;
   if (stages < 2) return -1002;  // rows too large for the smem ring: caller falls back
   const size_t smem = (size_t)stages * stage_bytes + 64;
   auto kern = fps_mf_sgd_tma_kernel<IdT, LPR>;

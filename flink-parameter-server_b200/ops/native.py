@@ -36,6 +36,8 @@ class ShardTableC(C.Structure):
         ("dim", C.c_int),
         ("stride", C.c_int),
         ("mode", C.c_int),
+        ("shard_shift", C.c_int),
+        ("pad_", C.c_int),
     ]
 
 
@@ -53,6 +55,7 @@ class MfArgsC(C.Structure):
         ("step", C.c_ulonglong),
         ("user_table", C.c_void_p),
         ("user_div", C.c_int),
+        ("user_shift", C.c_int),
         ("lr", C.c_float),
         ("err_mode", C.c_int),
         ("stats", C.c_void_p),
@@ -110,6 +113,11 @@ def sm_count(device: Optional[int] = None) -> int:
     if dev not in _sm_cache:
         _sm_cache[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
     return _sm_cache[dev]
+
+
+def log2_or_neg(n: int) -> int:
+    """log2(n) if n is a power of two, else -1 (kernels then use a real division)."""
+    return n.bit_length() - 1 if n > 0 and (n & (n - 1)) == 0 else -1
 
 
 def _id_bytes(ids: torch.Tensor) -> int:
@@ -230,11 +238,15 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.n_pos = users.numel(); a.neg_rate = int(neg_rate); a.num_items = int(max(num_items, 1))
     a.seed = seed & (2**64 - 1); a.step = int(step)
     a.user_table = user_table.data_ptr(); a.user_div = int(user_div)
+    a.user_shift = log2_or_neg(int(user_div))
     a.lr = float(lr); a.err_mode = int(err_mode)
     a.stats = stats.data_ptr() if stats is not None else None
     a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
     a.item_tab = item_tab
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "tma")
+    rv = os.environ.get("FPS_MF_REG_VARIANT")
+    if rv is not None:
+        lib().fps_set_mf_reg_variant(int(rv))
     if variant == "tma":
         code = lib().fps_mf_sgd_tma(C.byref(a), _id_bytes(users), int(max_inflight_rows),
                                     sm_count(users.device.index), _stream())

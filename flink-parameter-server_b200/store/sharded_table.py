@@ -62,6 +62,7 @@ class ShardedTable:
         tc.dim = self.dim
         tc.stride = self.stride
         tc.mode = self.mode
+        tc.shard_shift = native.log2_or_neg(self.world)
         self.table_c = tc
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.cuda_device)
 
