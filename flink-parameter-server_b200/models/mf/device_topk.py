@@ -1,0 +1,93 @@
+"""Device top-K recommendation (K6 / K12): pull query vectors from the PS, score them against the
+worker-local item table on the tcgen05 tensor cores, keep an exact top-K.
+
+Capability of ``psTopKGenerator`` / the generator half of ``psOnlineLearnerAndGenerator``
+(PSTopKGenerator.scala:47-107, PSTopKGeneratorWorker.scala:35-114): user vectors live on the PS,
+item vectors on the workers, every query is answered by every worker with its local top-``workerK``
+and the partial lists are merged (``merge_partial_topk`` = CollectTopKFromEachWorker).
+
+Algorithm (exact, tile-pruned -- the GPU-idiomatic replacement of the LEMP bucket scan):
+  pass 1  tensor-core GEMM, epilogue keeps only the per-(query, 128-item tile) maximum;
+  theta   K-th largest tile maximum per query  (a lower bound of the true K-th best score);
+  pass 2  same GEMM, epilogue appends every (score, item) >= theta  (a few x K candidates);
+  select  top-K of the candidates.
+Scores are TF32 products accumulated in FP32; ``rescore=True`` recomputes the K winners in full
+FP32 (ordering among near-ties may then differ from the TF32 ranking by < 1e-3 relative).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from ...ops import native
+from ...store.sharded_table import ShardedTable
+
+
+class DeviceTopK:
+    def __init__(self, items: torch.Tensor, max_batch_bytes: int = 512 << 20):
+        if items.dim() != 2 or items.shape[1] % 4 != 0:
+            raise ValueError("items must be [n_items, stride] with stride % 4 == 0")
+        self.items = items
+        self.n_items, self.stride = items.shape
+        self.n_tiles = (self.n_items + native.TOPK_TILE - 1) // native.TOPK_TILE
+        self.max_batch_bytes = max_batch_bytes
+
+    # -- raw scores (validation / tiny problems) ---------------------------------------------
+    def scores(self, *, q_ids=None, q_table: Optional[ShardedTable] = None, q_local=None) -> torch.Tensor:
+        n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
+        out = torch.empty((n_q, self.n_items), dtype=torch.float32, device=self.items.device)
+        native.topk_mma(self.items, 0, q_ids=q_ids, q_tab=q_table.table_c if q_table else None,
+                        q_local=q_local, out_scores=out)
+        return out
+
+    def topk(self, K: int, *, q_ids=None, q_table: Optional[ShardedTable] = None, q_local=None,
+             rescore: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns ``(scores [n_q, K'], item_rows [n_q, K'])`` best first, ``K' = min(K, n_items)``;
+        item_rows index the local item table."""
+        n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
+        Kp = min(K, self.n_items)
+        cap = min(self.n_items, max(Kp * native.TOPK_TILE, native.TOPK_TILE))
+        chunk = max(128, (self.max_batch_bytes // (cap * 8)) // 128 * 128)
+        outs, outi = [], []
+        dev = self.items.device
+        for a in range(0, n_q, chunk):
+            b = min(n_q, a + chunk)
+            ids = q_ids[a:b].contiguous() if q_ids is not None else None
+            ql = q_local[a:b].contiguous() if q_local is not None else None
+            tab = q_table.table_c if q_table is not None else None
+            n = b - a
+            tile_max = torch.empty((n, self.n_tiles), dtype=torch.float32, device=dev)
+            native.topk_mma(self.items, 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
+            if self.n_tiles >= Kp:
+                theta = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
+            else:
+                theta = torch.full((n,), -3.0e38, dtype=torch.float32, device=dev)
+            cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+            cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
+            ci = torch.empty((n, cap), dtype=torch.int32, device=dev)
+            native.topk_mma(self.items, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
+                            cand_count=cnt, cand_score=cs, cand_item=ci)
+            valid = torch.arange(cap, device=dev)[None, :] < cnt.clamp(max=cap)[:, None]
+            cs = torch.where(valid, cs, torch.full_like(cs, -3.0e38))
+            top = torch.topk(cs, Kp, dim=1)
+            rows = torch.gather(ci, 1, top.indices).to(torch.int64)
+            sc = top.values
+            if rescore:
+                q = (q_table.pull(ids) if ids is not None else ql[:, : self.stride])
+                q = torch.nn.functional.pad(q, (0, self.stride - q.shape[1]))
+                exact = torch.einsum("qd,qkd->qk", q, self.items[rows])
+                order = torch.argsort(exact, dim=1, descending=True)
+                sc, rows = torch.gather(exact, 1, order), torch.gather(rows, 1, order)
+            outs.append(sc); outi.append(rows)
+        return torch.cat(outs), torch.cat(outi)
+
+
+def merge_partial_topk(scores: torch.Tensor, items: torch.Tensor, K: int,
+                       seen_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K-way merge of per-worker partial lists ``[n_q, W*workerK]`` with an optional seen-item filter
+    (CollectTopKFromEachWorker.scala:41-56)."""
+    if seen_mask is not None:
+        scores = torch.where(seen_mask, torch.full_like(scores, -3.0e38), scores)
+    top = torch.topk(scores, min(K, scores.shape[1]), dim=1)
+    return top.values, torch.gather(items, 1, top.indices)

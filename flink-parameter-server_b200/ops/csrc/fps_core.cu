@@ -230,6 +230,12 @@ static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStrea
       case 2: return launch_mf<IdT, 16, 1, 8, 1>(a, max_inflight, num_sms, s);
       case 3: return launch_mf<IdT, 16, 1, 2, 4>(a, max_inflight, num_sms, s);
       case 4: return launch_mf<IdT, 16, 1, 6, 2>(a, max_inflight, num_sms, s);
+      case 5: return launch_mf<IdT, 16, 1, 2, 5>(a, max_inflight, num_sms, s);
+      case 6: return launch_mf<IdT, 16, 1, 2, 6>(a, max_inflight, num_sms, s);
+      case 7: return launch_mf<IdT, 16, 1, 1, 8>(a, max_inflight, num_sms, s);
+      case 8: return launch_mf<IdT, 16, 1, 3, 4>(a, max_inflight, num_sms, s);
+      case 9: return launch_mf<IdT, 8, 2, 2, 4>(a, max_inflight, num_sms, s);
+      case 10: return launch_mf<IdT, 8, 2, 1, 6>(a, max_inflight, num_sms, s);
       default: return launch_mf<IdT, 16, 1, 4, 2>(a, max_inflight, num_sms, s);
     }
   }

@@ -289,3 +289,68 @@ def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: to
                               int(local.shape[1]), C.c_void_p(score.data_ptr()),
                               sm_count(ids.device.index), _stream()), "pull_dot")
     _bump()
+
+
+class TopkArgsC(C.Structure):
+    """Mirror of ``struct TopkArgs`` (csrc/fps_topk_mma.cu)."""
+
+    _fields_ = [
+        ("q_ids", C.c_void_p),
+        ("q_local", C.c_void_p),
+        ("q_tab", ShardTableC),
+        ("n_queries", C.c_int),
+        ("n_items", C.c_int),
+        ("stride", C.c_int),
+        ("n_tiles", C.c_int),
+        ("tiles_per_split", C.c_int),
+        ("n_splits", C.c_int),
+        ("mode", C.c_int),
+        ("out_scores", C.c_void_p),
+        ("out_ld", C.c_longlong),
+        ("tile_max", C.c_void_p),
+        ("theta", C.c_void_p),
+        ("cand_count", C.c_void_p),
+        ("cand_score", C.c_void_p),
+        ("cand_item", C.c_void_p),
+        ("cand_cap", C.c_int),
+    ]
+
+
+TOPK_TILE = 128
+
+
+def topk_mma(items: torch.Tensor, mode: int, *, q_ids: Optional[torch.Tensor] = None,
+             q_tab: Optional[ShardTableC] = None, q_local: Optional[torch.Tensor] = None,
+             out_scores: Optional[torch.Tensor] = None, tile_max: Optional[torch.Tensor] = None,
+             theta: Optional[torch.Tensor] = None, cand_count: Optional[torch.Tensor] = None,
+             cand_score: Optional[torch.Tensor] = None, cand_item: Optional[torch.Tensor] = None) -> None:
+    """tcgen05 scoring kernel (K6): queries (pulled from ``q_tab`` by id, or ``q_local``) x local
+    ``items`` with a mode-dependent epilogue.  See csrc/fps_topk_mma.cu."""
+    _req(items, "items", torch.float32)
+    n_items, stride = items.shape
+    a = TopkArgsC()
+    if q_ids is not None:
+        _req(q_ids, "q_ids")
+        a.q_ids = q_ids.data_ptr(); a.q_tab = q_tab; n_q = q_ids.numel(); idb = _id_bytes(q_ids)
+        if q_tab.stride != stride:
+            raise ValueError("query table stride must equal item table stride")
+    else:
+        _req(q_local, "q_local", torch.float32)
+        if q_local.shape[1] != stride:
+            raise ValueError("q_local stride must equal item table stride")
+        a.q_ids = None; a.q_local = q_local.data_ptr(); n_q = q_local.shape[0]; idb = 4
+    a.n_queries = n_q; a.n_items = n_items; a.stride = stride; a.mode = int(mode)
+    if mode == 0:
+        _req(out_scores, "out_scores", torch.float32)
+        a.out_scores = out_scores.data_ptr(); a.out_ld = out_scores.stride(0)
+    elif mode == 1:
+        _req(tile_max, "tile_max", torch.float32)
+        assert tile_max.shape == (n_q, (n_items + TOPK_TILE - 1) // TOPK_TILE)
+        a.tile_max = tile_max.data_ptr()
+    else:
+        a.theta = theta.data_ptr(); a.cand_count = cand_count.data_ptr()
+        a.cand_score = cand_score.data_ptr(); a.cand_item = cand_item.data_ptr()
+        a.cand_cap = cand_score.shape[1]
+    _check(lib().fps_topk_mma(C.byref(a), C.c_void_p(items.data_ptr()), idb,
+                              sm_count(items.device.index), _stream()), "topk_mma")
+    _bump()
