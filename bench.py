@@ -46,6 +46,9 @@ def parse():
     p.add_argument("--lr", type=float, default=0.01)
     p.add_argument("--pull-limit", type=int, default=0, help="0 = hardware max rows in flight")
     p.add_argument("--host-buffers", type=int, default=6)
+    p.add_argument("--format", default="packed64", choices=["packed64", "arrays"],
+                   help="rating record format: packed64 = 8 B/update (user:26|item:22|fp16 rating), "
+                        "arrays = int32 user, int32 item, fp32 rating (12 B/update)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()
@@ -145,8 +148,11 @@ def main():
     for _ in range(a.host_buffers):
         u = torch.randint(0, n_local_users, (a.batch,), generator=g, dtype=torch.int32) * world + rank
         i = torch.randint(0, a.items, (a.batch,), generator=g, dtype=torch.int32)
-        r = torch.rand(a.batch, generator=g, dtype=torch.float32)
-        host.append((u.pin_memory(), i.pin_memory(), r.pin_memory()))
+        r = torch.rand(a.batch, generator=g, dtype=torch.float32).half().float()  # fp16-exact ratings
+        if a.format == "packed64" and a.impl == "fps_b200":
+            host.append((native.pack_ratings(u, i, r).pin_memory(),))
+        else:
+            host.append((u.pin_memory(), i.pin_memory(), r.pin_memory()))
     devb = [tuple(t.to(dev) for t in b) for b in host]
 
     def barrier():
@@ -228,6 +234,7 @@ def main():
                        "l2": "inputs larger than L2: 2.8 GB of factor tables accessed at random, "
                              f"{len(host)} distinct {h2d >> 20} MiB rating batches cycled",
                        "pull_limit": a.pull_limit or "hardware max rows in flight",
+                       "record_format": a.format if a.impl == "fps_b200" else "arrays",
                        "update_rule": "reference parity e=sigmoid(r-u.v), fp32 (reference: fp64 JVM)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms_max / a.steps,

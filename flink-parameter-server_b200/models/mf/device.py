@@ -69,8 +69,10 @@ class DeviceOnlineMF:
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
-    def step(self, users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor) -> None:
-        """Process one micro-batch of ratings whose users belong to this worker (async SGD)."""
+    def step(self, users: torch.Tensor, items: Optional[torch.Tensor] = None,
+             ratings: Optional[torch.Tensor] = None) -> None:
+        """Process one micro-batch of ratings whose users belong to this worker (async SGD).
+        ``step(packed)`` with a single int64 tensor takes packed64 records (``native.pack_ratings``)."""
         native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                             self.lr, err_mode=self.err_mode, neg_rate=self.neg,
                             num_items=self.num_items, seed=self.seed, step=self.step_no,
@@ -90,9 +92,9 @@ class DeviceOnlineMF:
         pending = []
         ring = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(4)]
         i = 0
-        for (u, it, r) in pf:
+        for batch in pf:
             self.stats.zero_()
-            self.step(u, it, r)
+            self.step(*batch)
             host = ring[i % len(ring)]
             host.copy_(self.stats, non_blocking=True)
             ev = torch.cuda.Event()

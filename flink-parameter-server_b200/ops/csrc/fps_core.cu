@@ -7,6 +7,7 @@
 // Reference behaviour being reproduced (not code): SimplePSLogic.scala:13-25 (init on
 // first pull, additive update), SGDUpdater.scala:5-14 (delta rule),
 // PSOnlineMatrixFactorizationWorker.scala:42-89 (worker step + negative sampling).
+#include <cuda_fp16.h>
 #include "fps_common.cuh"
 
 // ----------------------------------------------------------------------------------------
@@ -80,12 +81,14 @@ struct MfArgs {
   int user_shift;             // log2(user_div) if power of two, else -1
   float lr;
   int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual
+  int format;                 // 0: users/items/ratings arrays; 1: packed64 records in `users`
+                              //    (user:26 | item:22 | rating fp16:16) -- 8 B/update over PCIe
   float* stats;               // [0] += sum (r-u.v)^2, [1] += #updates
   int* nan_flag;              // set to 1 if a non-finite update was produced
   ShardTable item_tab;
 };
 
-template <typename IdT, int LPR, int VPL, int R, int MINB>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
 __global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
   const int lane = threadIdx.x & (LPR - 1);
@@ -119,10 +122,19 @@ __global__ void __launch_bounds__(256, MINB)
       IdT user = 0, item = 0;
       rt[r] = 0.f;
       if (ok[r]) {
-        user = users[pos];
-        item = items[pos];
+        float rating;
+        if (FMT == 1) {
+          const unsigned long long rec = reinterpret_cast<const unsigned long long*>(a.users)[pos];
+          user = (IdT)(rec >> 38);
+          item = (IdT)((rec >> 16) & 0x3FFFFFull);
+          rating = __half2float(__ushort_as_half((unsigned short)(rec & 0xFFFFull)));
+        } else {
+          user = users[pos];
+          item = items[pos];
+          rating = a.ratings[pos];
+        }
         if (j == 0) {
-          rt[r] = a.ratings[pos];
+          rt[r] = rating;
         } else {
           // K5: device-side negative sample, rejecting the positive item itself.
           Philox4 s = fps_philox((uint32_t)pos, (uint32_t)((unsigned long long)pos >> 32),
@@ -191,13 +203,13 @@ __global__ void __launch_bounds__(256, MINB)
   if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
 }
 
-template <typename IdT, int LPR, int VPL, int R, int MINB>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
   const int groups_per_block = threads / LPR;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB>, threads, 0);
+      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT>, threads, 0);
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
@@ -210,48 +222,46 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
   if (need < 1) need = 1;
   if (blocks > need) blocks = need;
-  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB><<<(int)blocks, threads, 0, stream>>>(a);
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT><<<(int)blocks, threads, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
 
 static int g_mf_reg_variant = 0;  // tuning knob: (rows in flight per lane-group, min blocks/SM)
 extern "C" void fps_set_mf_reg_variant(int v) { g_mf_reg_variant = v; }
 
-template <typename IdT>
+// Defaults come from the measured sweep in profiles/mf_fused_history.md: for 16-byte-per-lane rows
+// one row in flight per lane-group at full occupancy (8 CTAs/SM, 32 registers) wins on local HBM.
+template <typename IdT, int FMT>
 static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
   const int nvec = a.item_tab.stride >> 2;
-  if (nvec <= 1) return launch_mf<IdT, 1, 1, 4, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 2) return launch_mf<IdT, 2, 1, 4, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 4) return launch_mf<IdT, 4, 1, 4, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 8) return launch_mf<IdT, 8, 1, 4, 2>(a, max_inflight, num_sms, s);
+  const int v = g_mf_reg_variant;
+  if (nvec <= 1) return launch_mf<IdT, 1, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 2) return launch_mf<IdT, 2, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 4) return launch_mf<IdT, 4, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 8, FMT>(a, max_inflight, num_sms, s);
   if (nvec <= 16) {
-    switch (g_mf_reg_variant) {
-      case 1: return launch_mf<IdT, 16, 1, 4, 3>(a, max_inflight, num_sms, s);
-      case 2: return launch_mf<IdT, 16, 1, 8, 1>(a, max_inflight, num_sms, s);
-      case 3: return launch_mf<IdT, 16, 1, 2, 4>(a, max_inflight, num_sms, s);
-      case 4: return launch_mf<IdT, 16, 1, 6, 2>(a, max_inflight, num_sms, s);
-      case 5: return launch_mf<IdT, 16, 1, 2, 5>(a, max_inflight, num_sms, s);
-      case 6: return launch_mf<IdT, 16, 1, 2, 6>(a, max_inflight, num_sms, s);
-      case 7: return launch_mf<IdT, 16, 1, 1, 8>(a, max_inflight, num_sms, s);
-      case 8: return launch_mf<IdT, 16, 1, 3, 4>(a, max_inflight, num_sms, s);
-      case 9: return launch_mf<IdT, 8, 2, 2, 4>(a, max_inflight, num_sms, s);
-      case 10: return launch_mf<IdT, 8, 2, 1, 6>(a, max_inflight, num_sms, s);
-      default: return launch_mf<IdT, 16, 1, 4, 2>(a, max_inflight, num_sms, s);
+    switch (v) {
+      case 1: return launch_mf<IdT, 16, 1, 4, 3, FMT>(a, max_inflight, num_sms, s);
+      case 3: return launch_mf<IdT, 16, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
+      case 5: return launch_mf<IdT, 16, 1, 2, 5, FMT>(a, max_inflight, num_sms, s);
+      case 9: return launch_mf<IdT, 8, 2, 2, 4, FMT>(a, max_inflight, num_sms, s);
+      default: return launch_mf<IdT, 16, 1, 1, 8, FMT>(a, max_inflight, num_sms, s);
     }
   }
-  if (nvec <= 32) return launch_mf<IdT, 32, 1, 4, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 64) return launch_mf<IdT, 32, 2, 2, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 96) return launch_mf<IdT, 32, 3, 2, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 128) return launch_mf<IdT, 32, 4, 2, 2>(a, max_inflight, num_sms, s);
-  if (nvec <= 256) return launch_mf<IdT, 32, 8, 1, 2>(a, max_inflight, num_sms, s);
+  if (nvec <= 32) return launch_mf<IdT, 32, 1, 1, 8, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 64) return launch_mf<IdT, 32, 2, 1, 4, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 96) return launch_mf<IdT, 32, 3, 1, 4, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 128) return launch_mf<IdT, 32, 4, 1, 2, FMT>(a, max_inflight, num_sms, s);
+  if (nvec <= 256) return launch_mf<IdT, 32, 8, 1, 2, FMT>(a, max_inflight, num_sms, s);
   return -1000;  // dim > 1024 not supported by the fused MF kernel
 }
 
 extern "C" int fps_mf_sgd_fused(const MfArgs* args, int id_bytes, int max_inflight_rows,
                                 int num_sms, cudaStream_t stream) {
   if (args->n_pos <= 0) return 0;
-  if (id_bytes == 4) return dispatch_mf<int>(*args, max_inflight_rows, num_sms, stream);
-  if (id_bytes == 8) return dispatch_mf<long long>(*args, max_inflight_rows, num_sms, stream);
+  if (args->format == 1) return dispatch_mf<int, 1>(*args, max_inflight_rows, num_sms, stream);
+  if (id_bytes == 4) return dispatch_mf<int, 0>(*args, max_inflight_rows, num_sms, stream);
+  if (id_bytes == 8) return dispatch_mf<long long, 0>(*args, max_inflight_rows, num_sms, stream);
   return -1001;
 }
 

@@ -32,6 +32,7 @@ struct MfArgs {  // must match fps_core.cu
   int user_shift;
   float lr;
   int err_mode;
+  int format;
   float* stats;
   int* nan_flag;
   ShardTable item_tab;

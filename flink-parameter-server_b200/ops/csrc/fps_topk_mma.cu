@@ -26,9 +26,9 @@
 #define TK_M 128          // query rows per CTA (UMMA M)
 #define TK_N 128          // items per tile (UMMA N)
 #define TK_KB_FLOATS 32   // floats per 128-byte swizzle atom row
-#define TK_STAGES 4
+#define TK_MAX_STAGES 4
 #define TK_THREADS 256
-#define TK_MAX_KB 8       // dim <= 256
+#define TK_MAX_KB 4       // dim <= 128 (A block + >= 2 B stages must fit in 227 KB of smem)
 
 struct TopkArgs {
   const void* q_ids;        // [n_queries] ids of the query vectors in q_tab (null -> q_local)
@@ -41,6 +41,7 @@ struct TopkArgs {
   int tiles_per_split;
   int n_splits;
   int mode;
+  int n_stages;             // B-operand ring depth (2..4, from the smem budget)
   float* out_scores;        // mode 0: [n_queries, out_ld]
   long long out_ld;
   float* tile_max;          // mode 1: [n_queries, n_tiles]
@@ -133,10 +134,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
   const uint32_t kb_bytes = TK_M * 128;                         // one K block of a 128-row tile
   unsigned char* sA = tk_smem_raw;                              // [KB][128 rows][128 B]
   unsigned char* sB = sA + (size_t)KB * kb_bytes;               // [STAGES][KB][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)TK_STAGES * KB * kb_bytes);
+  const int NS = a.n_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NS * KB * kb_bytes);
   uint64_t* full = bars;                  // [STAGES] TMA -> MMA
-  uint64_t* empty = bars + TK_STAGES;     // [STAGES] MMA -> TMA
-  uint64_t* tfull = bars + 2 * TK_STAGES;   // [2] MMA -> epilogue
+  uint64_t* empty = bars + TK_MAX_STAGES;     // [STAGES] MMA -> TMA
+  uint64_t* tfull = bars + 2 * TK_MAX_STAGES;   // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
   const int row0 = qb * TK_M;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TK_STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       tk_mbar_init(&full[s], 1);
       tk_mbar_init(&empty[s], 1);
     }
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
     // =============================== TMA producer (items) ===============================
     if (lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % TK_STAGES;
-        const uint32_t ph = (uint32_t)((i / TK_STAGES) & 1);
+        const int s = i % NS;
+        const uint32_t ph = (uint32_t)((i / NS) & 1);
         tk_mbar_wait(&empty[s], ph ^ 1u);
         tk_mbar_expect_tx(&full[s], (uint32_t)KB * kb_bytes);
         const int item0 = (tile_begin + i) * TK_N;
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
                            ((uint32_t)(TK_M >> 4) << 24);
     if (lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % TK_STAGES;
-        const uint32_t ph = (uint32_t)((i / TK_STAGES) & 1);
+        const int s = i % NS;
+        const uint32_t ph = (uint32_t)((i / NS) & 1);
         const int acc = i & 1;
         const uint32_t aph = (uint32_t)((i >> 1) & 1);
         tk_mbar_wait(&tempty[acc], aph ^ 1u);  // epilogue drained this accumulator
@@ -330,7 +332,12 @@ extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, in
   if (splits < 1) splits = 1;
   a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
   a.n_splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
-  const size_t smem = (size_t)KB * TK_M * 128 * (1 + TK_STAGES) + 16 * 8 + 16 + 1024;
+  const size_t blk = (size_t)KB * TK_M * 128;
+  int stages = (int)((220 * 1024 - blk - 2048) / blk);
+  if (stages > TK_MAX_STAGES) stages = TK_MAX_STAGES;
+  if (stages < 2) return -1003;
+  a.n_stages = stages;
+  const size_t smem = blk * (1 + stages) + 16 * 8 + 16 + 1024;
   cudaError_t e;
   if (id_bytes == 8) {
     e = cudaFuncSetAttribute(fps_topk_mma_kernel<long long>,

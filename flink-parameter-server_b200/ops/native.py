@@ -58,6 +58,7 @@ class MfArgsC(C.Structure):
         ("user_shift", C.c_int),
         ("lr", C.c_float),
         ("err_mode", C.c_int),
+        ("format", C.c_int),
         ("stats", C.c_void_p),
         ("nan_flag", C.c_void_p),
         ("item_tab", ShardTableC),
@@ -225,16 +226,27 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  kernel: Optional[str] = None) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
-    ``kernel="tma"`` (default): warp-specialised TMA/mbarrier pipeline (csrc/fps_mf_tma.cu);
-    ``kernel="reg"``: register-staged variant (csrc/fps_core.cu)."""
-    _req(users, "users"); _req(items, "items"); _req(ratings, "ratings", torch.float32)
+    ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
+    ``kernel="tma"``: warp-specialised TMA/mbarrier pipeline (csrc/fps_mf_tma.cu) -- slower for
+    256-byte rows, kept for large rows (measurements: profiles/mf_fused_history.md).
+    ``items=None`` means ``users`` holds packed64 records (see :func:`pack_ratings`)."""
+    _req(users, "users")
     _req(user_table, "user_table", torch.float32)
-    if users.dtype != items.dtype:
-        raise TypeError("users and items must share an integer dtype")
+    packed = items is None
+    if packed:
+        if users.dtype != torch.int64:
+            raise TypeError("packed rating records must be an int64 tensor (see pack_ratings)")
+    else:
+        _req(items, "items"); _req(ratings, "ratings", torch.float32)
+        if users.dtype != items.dtype:
+            raise TypeError("users and items must share an integer dtype")
     if user_table.shape[1] != item_tab.stride:
         raise ValueError("user table stride must equal item table stride")
     a = MfArgsC()
-    a.users = users.data_ptr(); a.items = items.data_ptr(); a.ratings = ratings.data_ptr()
+    a.users = users.data_ptr()
+    a.items = None if packed else items.data_ptr()
+    a.ratings = None if packed else ratings.data_ptr()
+    a.format = 1 if packed else 0
     a.n_pos = users.numel(); a.neg_rate = int(neg_rate); a.num_items = int(max(num_items, 1))
     a.seed = seed & (2**64 - 1); a.step = int(step)
     a.user_table = user_table.data_ptr(); a.user_div = int(user_div)
@@ -243,7 +255,9 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.stats = stats.data_ptr() if stats is not None else None
     a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
     a.item_tab = item_tab
-    variant = kernel or os.environ.get("FPS_MF_KERNEL", "tma")
+    variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
+    if packed:
+        variant = "reg"
     rv = os.environ.get("FPS_MF_REG_VARIANT")
     if rv is not None:
         lib().fps_set_mf_reg_variant(int(rv))
@@ -254,9 +268,21 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
             _check(code, "mf_sgd_tma")
             _bump()
             return
-    _check(lib().fps_mf_sgd_fused(C.byref(a), _id_bytes(users), int(max_inflight_rows),
+    _check(lib().fps_mf_sgd_fused(C.byref(a), 4 if packed else _id_bytes(users), int(max_inflight_rows),
                                   sm_count(users.device.index), _stream()), "mf_sgd_fused")
     _bump()
+
+
+PACK_USER_BITS, PACK_ITEM_BITS = 26, 22
+
+
+def pack_ratings(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor) -> torch.Tensor:
+    """Pack ``(user, item, rating)`` into one int64 per rating: ``user:26 | item:22 | fp16 rating:16``
+    -- 8 bytes per update over PCIe instead of 12.  Limits: user < 2^26, item < 2^22."""
+    if int(users.max()) >= 1 << PACK_USER_BITS or int(items.max()) >= 1 << PACK_ITEM_BITS:
+        raise ValueError("ids exceed the packed64 record range (user < 2^26, item < 2^22)")
+    r16 = ratings.to(torch.float16).view(torch.int16).to(torch.int64) & 0xFFFF
+    return (users.to(torch.int64) << 38) | (items.to(torch.int64) << 16) | r16
 
 
 def pull_gather(tab: ShardTableC, ids: torch.Tensor, out: torch.Tensor, touch: bool = False) -> None:
@@ -353,4 +379,40 @@ def topk_mma(items: torch.Tensor, mode: int, *, q_ids: Optional[torch.Tensor] = 
         a.cand_cap = cand_score.shape[1]
     _check(lib().fps_topk_mma(C.byref(a), C.c_void_p(items.data_ptr()), idb,
                               sm_count(items.device.index), _stream()), "topk_mma")
+    _bump()
+
+
+class PaArgsC(C.Structure):
+    """Mirror of ``struct PaArgs`` (csrc/fps_pa.cu)."""
+
+    _fields_ = [
+        ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("values", C.c_void_p),
+        ("labels", C.c_void_p), ("pred", C.c_void_p), ("loss", C.c_void_p), ("cost", C.c_void_p),
+        ("n", C.c_longlong), ("binary", C.c_int), ("num_labels", C.c_int), ("algo", C.c_int),
+        ("aggressiveness", C.c_float), ("nan_flag", C.c_void_p), ("tab", ShardTableC),
+    ]
+
+
+PA_ALGOS = {"PA": 0, "PAI": 1, "PAII": 2, "PB": 3, "ML": 4}
+PA_UNLABELLED = -(2 ** 31)
+
+
+def pa_step(tab: ShardTableC, row_ptr: torch.Tensor, col_idx: torch.Tensor, values: torch.Tensor,
+            labels: torch.Tensor, pred: torch.Tensor, *, binary: bool, num_labels: int, algo: str,
+            aggressiveness: float = 0.0, cost: Optional[torch.Tensor] = None,
+            loss: Optional[torch.Tensor] = None, nan_flag: Optional[torch.Tensor] = None) -> None:
+    """Fused passive-aggressive step over a CSR micro-batch (K7).  See csrc/fps_pa.cu."""
+    _req(row_ptr, "row_ptr", torch.int64); _req(col_idx, "col_idx"); _req(values, "values", torch.float32)
+    _req(labels, "labels", torch.int32); _req(pred, "pred", torch.int32)
+    a = PaArgsC()
+    a.row_ptr = row_ptr.data_ptr(); a.col_idx = col_idx.data_ptr(); a.values = values.data_ptr()
+    a.labels = labels.data_ptr(); a.pred = pred.data_ptr()
+    a.loss = loss.data_ptr() if loss is not None else None
+    a.cost = cost.data_ptr() if cost is not None else None
+    a.n = labels.numel(); a.binary = int(binary); a.num_labels = int(num_labels)
+    a.algo = PA_ALGOS[algo]; a.aggressiveness = float(aggressiveness)
+    a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
+    a.tab = tab
+    _check(lib().fps_pa_step(C.byref(a), _id_bytes(col_idx), sm_count(values.device.index), _stream()),
+           "pa_step")
     _bump()

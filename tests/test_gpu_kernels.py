@@ -171,3 +171,23 @@ def test_fit_stream_end_to_end(dev):
     assert all(c == 4096 for _, c in res)
     assert all(np.isfinite(s) for s, _ in res)
     m.close()
+
+
+def test_packed64_records_equal_array_inputs(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+    from fps_b200.ops import native
+
+    nu, ni, k, b = 50000, 30000, 64, 20000
+    g = torch.Generator().manual_seed(3)
+    users = torch.randperm(nu, generator=g)[:b].int()
+    items = torch.randperm(ni, generator=g)[:b].int()
+    ratings = torch.rand(b, generator=g).half().float()
+    m1 = DeviceOnlineMF(nu, ni, k, learning_rate=0.05, seed=5, kernel="reg")
+    m2 = DeviceOnlineMF(nu, ni, k, learning_rate=0.05, seed=5, kernel="reg")
+    m1.step(users.cuda(), items.cuda(), ratings.cuda())
+    m2.step(native.pack_ratings(users, items, ratings).cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(m1.users, m2.users) and torch.equal(m1.items.local, m2.items.local)
+    with pytest.raises(ValueError):
+        native.pack_ratings(torch.tensor([1 << 26]), torch.tensor([0]), torch.tensor([1.0]))
+    m1.close(); m2.close()
