@@ -1,0 +1,139 @@
+"""Device tier of the streaming sketches: packed sketches in HBM shards, updates as one-sided
+reductions over NVLink (ops/csrc/fps_sketch.cu), queries as popcount / int-dot scans + top-K merge.
+
+Keys (word hashes, arbitrary ints or strings) are interned to dense slot ids on the host
+(:class:`KeyInterner`); slot ``s`` lives on shard ``s % G`` like every other table.
+``hash64`` is shared with the host tier so a device-built sketch equals the host-built one.
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ...ops import native
+from ...store.sharded_table import ShardedTable
+from .hashing import hash64, java_string_hash
+from .utils import merge_topk
+
+
+class KeyInterner:
+    """Opaque key -> dense int slot (string / opaque ids)."""
+
+    def __init__(self):
+        self.slot: Dict[Hashable, int] = {}
+        self.keys: List[Hashable] = []
+
+    def __call__(self, key: Hashable) -> int:
+        s = self.slot.get(key)
+        if s is None:
+            s = len(self.keys)
+            self.slot[key] = s
+            self.keys.append(key)
+        return s
+
+    def __len__(self):
+        return len(self.keys)
+
+
+class DeviceSketch:
+    """kind in {"bloom", "tow", "minhash"}; ``capacity`` = max number of distinct keys."""
+
+    def __init__(self, kind: str, capacity: int, num_hashes: int, array_size: int = 0, group=None,
+                 device: Optional[int] = None):
+        self.kind, self.num_hashes, self.array_size = kind, int(num_hashes), int(array_size)
+        if kind == "bloom":
+            self.words = (self.array_size + 31) // 32
+        elif kind == "tow":
+            self.words = self.num_hashes
+        elif kind == "minhash":
+            self.words = 2 * self.num_hashes
+        else:
+            raise ValueError(kind)
+        self.table = ShardedTable(capacity, self.words, group=group, device=device, init="zeros")
+        self.dev = self.table.cuda_device
+        self.rows_i32 = self.table.local.view(torch.int32)
+        if kind == "minhash":
+            self.rows_i32.fill_(-1)  # all-ones u64 = +inf for the min reduction
+            self.table.barrier()
+        self.interner = KeyInterner()
+
+    # -- train: (tweetId, [words]) records ---------------------------------------------------
+    def update(self, records: Iterable[Tuple[object, Sequence[str]]]) -> None:
+        keys, tweets = [], []
+        for rec in records:
+            tid = int(rec[0])
+            for w in rec[1]:
+                keys.append(self.interner(java_string_hash(w)))
+                tweets.append(tid)
+        if not keys:
+            return
+        k = torch.tensor(keys, dtype=torch.int32).to(self.dev, non_blocking=True)
+        t = torch.tensor(tweets, dtype=torch.int64).to(self.dev, non_blocking=True)
+        native.sketch_update(self.table.table_c, self.kind, k, t, self.num_hashes, self.array_size)
+
+    # -- export (the close() dump of the *PSLogic classes) -------------------------------------
+    def model(self) -> List[Tuple[int, object]]:
+        torch.cuda.synchronize()
+        self.table.barrier()
+        ids = self.table.local_ids().cpu().tolist()
+        rows = self.rows_i32.cpu().numpy()
+        out = []
+        for slot, id_ in enumerate(ids):
+            if id_ >= len(self.interner):
+                continue
+            key = self.interner.keys[id_]
+            r = rows[slot, : self.words]
+            if self.kind == "bloom":
+                bits = np.unpackbits(r.view(np.uint8), bitorder="little")[: self.array_size]
+                out.append((key, frozenset(np.nonzero(bits)[0].tolist())))
+            elif self.kind == "tow":
+                out.append((key, r.astype(np.int64).tolist()))
+            else:
+                packed = r.view(np.uint64)
+                out.append((key, [int(p & np.uint64(0xFFFFFFFF)) for p in packed]))
+        return out
+
+    # -- predict: co-occurrence top-K of a query word against the local shard -----------------
+    def query_local(self, word: str, K: int) -> List[Tuple[float, int]]:
+        key = java_string_hash(word)
+        slot = self.interner.slot.get(key)
+        if slot is None:
+            return []
+        q = self.table.pull(torch.tensor([slot], device=self.dev)).view(torch.int32)[0].contiguous()
+        n_local = self.rows_i32.shape[0]
+        ids = self.table.local_ids()
+        valid = ids < len(self.interner)
+        if self.kind == "bloom":
+            est = torch.empty(n_local, dtype=torch.float32, device=self.dev)
+            native.bloom_query(self.rows_i32, self.words, q, float(self.array_size),
+                               float(self.num_hashes), est)
+        elif self.kind == "tow":
+            est = (self.rows_i32[:, : self.words].double() @ q[: self.words].double()) / self.words
+            est = est.float()
+        else:
+            a = self.rows_i32[:, : self.words].view(torch.int64)[:, : self.num_hashes] & 0xFFFFFFFF
+            b = q[: self.words].view(torch.int64)[: self.num_hashes] & 0xFFFFFFFF
+            est = (a == b[None, :]).float().mean(1)
+        est = torch.where(valid, est, torch.full_like(est, -3.0e38))
+        k = min(K, int(valid.sum().item()))
+        top = torch.topk(est, k)
+        keys = [self.interner.keys[i] for i in ids[top.indices].cpu().tolist()]
+        return list(zip(top.values.cpu().tolist(), keys))
+
+    def close(self):
+        self.table.close()
+
+
+# host oracles (same hash family as the kernels) ----------------------------------------------
+def bloom_positions64(tweet_id: int, num_hashes: int, array_size: int) -> List[int]:
+    return [hash64(tweet_id, i) % array_size for i in range(num_hashes)]
+
+
+def tow_bits64(tweet_id: int, num_hashes: int) -> List[int]:
+    return [1 if (hash64(tweet_id, j >> 6) >> (j & 63)) & 1 else -1 for j in range(num_hashes)]
+
+
+def minhash_packed64(tweet_id: int, num_hashes: int) -> List[int]:
+    return [((hash64(tweet_id, j) >> 32) << 32) | (tweet_id & 0xFFFFFFFF) for j in range(num_hashes)]

@@ -416,3 +416,29 @@ def pa_step(tab: ShardTableC, row_ptr: torch.Tensor, col_idx: torch.Tensor, valu
     _check(lib().fps_pa_step(C.byref(a), _id_bytes(col_idx), sm_count(values.device.index), _stream()),
            "pa_step")
     _bump()
+
+
+SKETCH_KINDS = {"bloom": 0, "tow": 1, "minhash": 2}
+
+
+def sketch_update(tab: ShardTableC, kind: str, keys: torch.Tensor, tweets: torch.Tensor,
+                  num_hashes: int, array_size: int = 0) -> None:
+    """Sketch push fused with its update (red.or / red.add.s32 / red.min.u64).  csrc/fps_sketch.cu."""
+    _req(keys, "keys", torch.int32); _req(tweets, "tweets", torch.int64)
+    assert keys.numel() == tweets.numel()
+    _check(lib().fps_sketch_update(C.byref(tab), SKETCH_KINDS[kind], C.c_void_p(keys.data_ptr()),
+                                   C.c_void_p(tweets.data_ptr()), C.c_longlong(keys.numel()),
+                                   int(num_hashes), int(array_size), sm_count(keys.device.index),
+                                   _stream()), "sketch_update")
+    _bump()
+
+
+def bloom_query(local_rows: torch.Tensor, n_words: int, query: torch.Tensor, m: float, k: float,
+                est: torch.Tensor) -> None:
+    _req(local_rows, "local_rows", torch.int32); _req(query, "query", torch.int32)
+    _req(est, "est", torch.float32)
+    _check(lib().fps_bloom_query(C.c_void_p(local_rows.data_ptr()), C.c_longlong(local_rows.shape[0]),
+                                 int(local_rows.shape[1]), int(n_words), C.c_void_p(query.data_ptr()),
+                                 C.c_float(m), C.c_float(k), C.c_void_p(est.data_ptr()),
+                                 sm_count(local_rows.device.index), _stream()), "bloom_query")
+    _bump()
