@@ -1,0 +1,387 @@
+// Message tier on the device: peer-memory request / response rings, a persistent server kernel and
+// a device-side credit counter (pull limiter).
+//
+// This is the B200 replacement of the reference's iteration feedback edge (FPS:447-480) for the
+// stores that need *logic* on the server (per-key locks, non-commutative paramUpdate): the fused
+// kernels of fps_core.cu cover additive updates with zero messages, everything else goes through
+// these rings.
+//
+//   worker w  --(request ring  Req[s][w], lives in shard s's HBM, written over NVLink)-->  shard s
+//   shard  s  --(response ring Resp[w][s], lives in worker w's HBM, written over NVLink)--> worker w
+//
+// Rings are single-producer / single-consumer, entries are published with st.release.sys and
+// observed with ld.acquire.sys, so FIFO order per (producer, consumer) pair -- the ordering the
+// reference's per-id answer queues rely on -- holds by construction.
+//
+// Server ops (the "registered-op table"): PULL answers the row; PUSH applies ADD / ASSIGN / MAX / MIN.
+// Lock modes reproduce LockPSLogicA / LockPSLogicB (M/server/LockPSLogicA.scala:13-46,
+// LockPSLogicB.scala:15-50): a pull takes the row lock, later pulls queue (B: one entry per worker),
+// a push applies the update and either unlocks or hands the fresh value to the queue head.
+//
+// Credit counter = addPullLimiter (WL:196-250) on the device: at most `limit` unanswered pulls;
+// excess pull ids wait in a FIFO spill queue; every consumed answer releases one credit and issues
+// exactly one queued pull (contract of T/WorkerLogicTest.scala:34-46, tests/test_gpu_rings.py).
+//
+// Every spin loop is bounded (FPS_SPIN_LIMIT) and reports through an error word instead of hanging.
+#include "fps_common.cuh"
+
+#define FPS_SPIN_LIMIT (1u << 22)
+#define RING_MAX_PEERS 16
+
+enum RingOp : int { OP_PULL = 1, OP_PUSH = 2 };
+enum UpdateOp : int { UPD_ADD = 0, UPD_ASSIGN = 1, UPD_MAX = 2, UPD_MIN = 3 };
+enum LockMode : int { LOCK_NONE = 0, LOCK_A = 1, LOCK_B = 2 };
+enum RingErr : int { ERR_NONE = 0, ERR_SPIN = 1, ERR_PUSH_UNKNOWN = 2, ERR_POOL = 3 };
+
+struct RingHdr {               // 128 bytes, producer and consumer words on separate lines
+  unsigned long long head;     // next slot to write  (producer)
+  unsigned long long pad0[7];
+  unsigned long long tail;     // next slot to read   (consumer)
+  unsigned long long pad1[7];
+};
+struct Entry {                 // followed by `stride` floats of payload
+  int op;
+  int peer;                    // requests: asking worker; responses: answering shard
+  long long id;
+  unsigned int tag;
+  unsigned int pad;
+};
+
+struct RingSet {               // one direction of one rank's rings, as seen by one side
+  unsigned char* base[RING_MAX_PEERS];   // ring base address per peer (header + entries)
+  int n_peers;
+  int capacity;                // entries per ring (power of two)
+  int stride;                  // payload floats
+  int entry_bytes;             // sizeof(Entry) + 4 * stride, multiple of 16
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ RingHdr* ring_hdr(const RingSet& r, int peer) {
+  return reinterpret_cast<RingHdr*>(r.base[peer]);
+}
+__device__ __forceinline__ Entry* ring_entry(const RingSet& r, int peer, unsigned long long slot) {
+  return reinterpret_cast<Entry*>(r.base[peer] + sizeof(RingHdr) +
+                                  (size_t)(slot & (unsigned long long)(r.capacity - 1)) * r.entry_bytes);
+}
+__device__ __forceinline__ float* entry_payload(Entry* e) {
+  return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + sizeof(Entry));
+}
+
+// Warp-cooperative enqueue (single producer per ring).  Returns false on spin-limit.
+__device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long id, unsigned tag,
+                         const float* payload, int lane, int* err) {
+  RingHdr* h = ring_hdr(r, peer);
+  unsigned long long head = 0;
+  int ok = 1;
+  if (lane == 0) {
+    head = h->head;  // only this producer writes head: a plain read of our own last value
+    unsigned spins = 0;
+    while (head - ld_acquire_sys(&h->tail) >= (unsigned long long)r.capacity) {
+      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+      __nanosleep(64);
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  head = __shfl_sync(0xffffffffu, head, 0);
+  if (!ok) { if (lane == 0) atomicExch(err, ERR_SPIN); return false; }
+  Entry* e = ring_entry(r, peer, head);
+  if (lane == 0) { e->op = op; e->peer = self; e->id = id; e->tag = tag; e->pad = 0; }
+  float* dst = entry_payload(e);
+  for (int q = lane; q < r.stride; q += 32) dst[q] = payload ? payload[q] : 0.f;
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();
+    st_release_sys(&h->head, head + 1);
+  }
+  return true;
+}
+
+// ============================================================================================
+// persistent server kernel
+// ============================================================================================
+struct LockNode { int worker; unsigned tag; int next; };
+struct ServerArgs {
+  RingSet req;        // my request rings (local memory), one per worker
+  RingSet resp;       // every worker's response ring for me (peer memory)
+  ShardTable tab;     // the table; only rows of shard `self` are touched
+  int self;           // this shard's index
+  int update_op;      // UpdateOp
+  int lock_mode;      // LockMode
+  int* lock_state;    // [rows]: 0 unlocked, 1 locked                    (lock modes)
+  int* lock_mutex;    // [rows]: spin mutex protecting the waiter list    (lock modes)
+  int* wait_head;     // [rows]: head of the waiter list (-1 = empty), tail appended by walking
+  LockNode* pool;     // waiter node pool
+  int* pool_next;     // bump allocator over the pool (nodes are recycled through free_head)
+  int* free_head;
+  int pool_size;
+  unsigned int* touched;  // [rows/32] bitmap: row ever pulled (lazy-init "exists" semantics)
+  volatile int* stop;     // host sets to 1 to drain and exit
+  int* err;
+  unsigned long long* counters;  // [0] pulls served, [1] pushes applied, [2] answers sent
+};
+
+__device__ __forceinline__ float* local_row(const ServerArgs& a, long long id, long long& slot) {
+  int owner;
+  fps_locate(a.tab, id, owner, slot);
+  return a.tab.base[a.self] + slot * (long long)a.tab.stride;
+}
+
+__device__ void apply_update(const ServerArgs& a, float* row, const float* delta, int lane) {
+  for (int q = lane; q < a.tab.stride; q += 32) {
+    const float d = delta[q];
+    if (a.update_op == UPD_ADD) {
+      atomicAdd(row + q, d);
+    } else if (a.update_op == UPD_ASSIGN) {
+      row[q] = d;
+    } else {
+      int* p = reinterpret_cast<int*>(row + q);
+      int old = *p, assumed;
+      do {
+        assumed = old;
+        const float cur = __int_as_float(assumed);
+        const float nv = (a.update_op == UPD_MAX) ? fmaxf(cur, d) : fminf(cur, d);
+        old = atomicCAS(p, assumed, __float_as_int(nv));
+      } while (old != assumed);
+    }
+  }
+  __syncwarp();
+  __threadfence();
+}
+
+__device__ bool answer(const ServerArgs& a, int worker, long long id, unsigned tag, const float* row,
+                       int lane) {
+  const bool ok = ring_put(a.resp, worker, OP_PULL, a.self, id, tag, row, lane, a.err);
+  if (ok && lane == 0) atomicAdd(a.counters + 2, 1ull);
+  return ok;
+}
+
+__global__ void __launch_bounds__(32 * RING_MAX_PEERS)
+    fps_server_loop_kernel(const __grid_constant__ ServerArgs a) {
+  const int w = threadIdx.x >> 5;  // this warp serves the ring of worker w
+  const int lane = threadIdx.x & 31;
+  if (w >= a.req.n_peers) return;
+  RingHdr* h = ring_hdr(a.req, w);
+  unsigned long long tail = h->tail;
+  unsigned idle = 0;
+  while (true) {
+    const unsigned long long head = ld_acquire_sys(&h->head);
+    if (tail == head) {
+      if (*a.stop) break;
+      if (++idle > 64) __nanosleep(256);
+      continue;
+    }
+    idle = 0;
+    Entry* e = ring_entry(a.req, w, tail);
+    const int op = e->op;
+    const long long id = e->id;
+    const unsigned tag = e->tag;
+    const int worker = e->peer;
+    long long slot;
+    float* row = local_row(a, id, slot);
+    if (a.lock_mode == LOCK_NONE) {
+      if (op == OP_PULL) {
+        if (lane == 0 && a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
+        if (!answer(a, worker, id, tag, row, lane)) return;
+        if (lane == 0) atomicAdd(a.counters + 0, 1ull);
+      } else {
+        apply_update(a, row, entry_payload(e), lane);
+        if (lane == 0) {
+          if (a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
+          atomicAdd(a.counters + 1, 1ull);
+        }
+      }
+    } else {
+      // ---- LockPSLogicA / B: all state changes of one row are serialised by a spin mutex ----
+      int granted = 0, hand_worker = -1;
+      unsigned hand_tag = 0;
+      if (lane == 0) {
+        unsigned spins = 0;
+        while (atomicCAS(a.lock_mutex + slot, 0, 1) != 0)
+          if (++spins > FPS_SPIN_LIMIT) { atomicExch(a.err, ERR_SPIN); break; }
+        __threadfence();
+        if (op == OP_PULL) {
+          if (a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
+          if (a.lock_state[slot] == 0) {
+            a.lock_state[slot] = 1;
+            granted = 1;
+          } else {
+            bool dup = false;
+            int last = -1;
+            for (int n = a.wait_head[slot]; n >= 0; n = a.pool[n].next) {
+              if (a.lock_mode == LOCK_B && a.pool[n].worker == worker) dup = true;
+              last = n;
+            }
+            if (!dup) {
+              const int node = atomicAdd(a.pool_next, 1);  // bump allocation (pool sized by the host)
+              if (node >= a.pool_size) {
+                atomicExch(a.err, ERR_POOL);
+              } else {
+                a.pool[node].worker = worker;
+                a.pool[node].tag = tag;
+                a.pool[node].next = -1;
+                if (last < 0) a.wait_head[slot] = node; else a.pool[last].next = node;
+              }
+            }
+          }
+        } else {
+          const bool known = a.touched == nullptr ||
+                             ((a.touched[slot >> 5] >> (slot & 31)) & 1u) != 0;
+          if (!known) atomicExch(a.err, ERR_PUSH_UNKNOWN);  // "Not existed model ..." (LockPSLogicA:43)
+        }
+      }
+      granted = __shfl_sync(0xffffffffu, granted, 0);
+      if (op == OP_PULL) {
+        if (lane == 0) { __threadfence(); atomicExch(a.lock_mutex + slot, 0); }
+        if (granted && !answer(a, worker, id, tag, row, lane)) return;
+        if (lane == 0) atomicAdd(a.counters + 0, 1ull);
+      } else {
+        apply_update(a, row, entry_payload(e), lane);
+        if (lane == 0) {
+          const int n = a.wait_head[slot];
+          if (n < 0) {
+            a.lock_state[slot] = 0;                 // queue empty -> unlock
+          } else {
+            hand_worker = a.pool[n].worker;         // hand over to the head, stay locked
+            hand_tag = a.pool[n].tag;
+            a.wait_head[slot] = a.pool[n].next;
+          }
+          __threadfence();
+          atomicExch(a.lock_mutex + slot, 0);
+          atomicAdd(a.counters + 1, 1ull);
+        }
+        hand_worker = __shfl_sync(0xffffffffu, hand_worker, 0);
+        hand_tag = __shfl_sync(0xffffffffu, hand_tag, 0);
+        if (hand_worker >= 0 && !answer(a, hand_worker, id, hand_tag, row, lane)) return;
+      }
+    }
+    ++tail;
+    if (lane == 0) st_release_sys(&h->tail, tail);
+    __syncwarp();
+  }
+}
+
+extern "C" int fps_server_loop_launch(const ServerArgs* a, cudaStream_t stream) {
+  fps_server_loop_kernel<<<1, 32 * a->req.n_peers, 0, stream>>>(*a);
+  return (int)cudaGetLastError();
+}
+
+// ============================================================================================
+// worker side: credit counter + issue / collect kernels (one warp each)
+// ============================================================================================
+struct ClientState {            // device-resident, one per worker
+  int credits;                  // remaining pull credits (pullLimit - in flight)
+  int limit;
+  unsigned long long issued;    // pulls actually sent  (== the mock's pullCounter in the unit test)
+  unsigned long long spill_head, spill_tail;  // FIFO of pull ids waiting for a credit
+  unsigned int next_tag;
+  int err;
+};
+struct ClientArgs {
+  RingSet req;        // request rings of every shard for me (peer memory), indexed by shard
+  RingSet resp;       // my response rings (local memory), indexed by shard
+  ShardTable tab;     // only used for id -> owner shard
+  ClientState* st;
+  long long* spill;   // [spill_cap] ids
+  int spill_cap;
+  int self;           // worker index
+};
+
+__device__ __forceinline__ int owner_of(const ShardTable& t, long long id) {
+  int owner; long long slot;
+  fps_locate(t, id, owner, slot);
+  return owner;
+}
+
+__device__ bool issue_pull(const ClientArgs& a, long long id, int lane) {
+  unsigned tag = 0;
+  if (lane == 0) { tag = a.st->next_tag++; }
+  tag = __shfl_sync(0xffffffffu, tag, 0);
+  const bool ok = ring_put(a.req, owner_of(a.tab, id), OP_PULL, a.self, id, tag, nullptr, lane, &a.st->err);
+  if (ok && lane == 0) a.st->issued++;
+  return ok;
+}
+
+// pulls: limited by the credit counter, excess ids spill FIFO.  pushes: never limited.
+__global__ void __launch_bounds__(32)
+    fps_client_issue_kernel(const __grid_constant__ ClientArgs a, const long long* __restrict__ ids,
+                            const float* __restrict__ deltas, int n, int op) {
+  const int lane = threadIdx.x;
+  for (int i = 0; i < n; ++i) {
+    const long long id = ids[i];
+    if (op == OP_PUSH) {
+      if (!ring_put(a.req, owner_of(a.tab, id), OP_PUSH, a.self, id, 0u,
+                    deltas + (size_t)i * a.req.stride, lane, &a.st->err))
+        return;
+      continue;
+    }
+    int take = 0;
+    if (lane == 0) {
+      if (a.st->credits > 0) { a.st->credits--; take = 1; }
+      else if (a.st->spill_tail - a.st->spill_head < (unsigned long long)a.spill_cap)
+        a.spill[a.st->spill_tail++ % a.spill_cap] = id;
+      else a.st->err = ERR_POOL;
+    }
+    take = __shfl_sync(0xffffffffu, take, 0);
+    if (take && !issue_pull(a, id, lane)) return;
+  }
+}
+
+// Drain up to max_n answers: copy them out, release one credit each and issue ONE spilled pull.
+__global__ void __launch_bounds__(32)
+    fps_client_collect_kernel(const __grid_constant__ ClientArgs a, long long* __restrict__ out_ids,
+                              float* __restrict__ out_vals, int max_n, int* __restrict__ n_out) {
+  const int lane = threadIdx.x;
+  int got = 0;
+  for (int s = 0; s < a.resp.n_peers && got < max_n; ++s) {
+    RingHdr* h = ring_hdr(a.resp, s);
+    unsigned long long tail = h->tail;
+    while (got < max_n) {
+      const unsigned long long head = ld_acquire_sys(&h->head);
+      if (tail == head) break;
+      Entry* e = ring_entry(a.resp, s, tail);
+      if (lane == 0) out_ids[got] = e->id;
+      const float* src = entry_payload(e);
+      for (int q = lane; q < a.resp.stride; q += 32) out_vals[(size_t)got * a.resp.stride + q] = src[q];
+      __syncwarp();
+      ++tail; ++got;
+      long long queued = -1;
+      if (lane == 0) {
+        st_release_sys(&h->tail, tail);
+        a.st->credits++;                                   // pullCounter -= 1
+        if (a.st->spill_head != a.st->spill_tail) {        // one queued pull per answer
+          queued = a.spill[a.st->spill_head++ % a.spill_cap];
+          a.st->credits--;
+        }
+      }
+      queued = __shfl_sync(0xffffffffu, queued, 0);
+      if (queued >= 0 && !issue_pull(a, queued, lane)) { if (lane == 0) *n_out = got; return; }
+    }
+  }
+  if (lane == 0) *n_out = got;
+}
+
+extern "C" int fps_client_issue(const ClientArgs* a, const long long* ids, const float* deltas, int n,
+                                int op, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  fps_client_issue_kernel<<<1, 32, 0, stream>>>(*a, ids, deltas, n, op);
+  return (int)cudaGetLastError();
+}
+extern "C" int fps_client_collect(const ClientArgs* a, long long* out_ids, float* out_vals, int max_n,
+                                  int* n_out, cudaStream_t stream) {
+  fps_client_collect_kernel<<<1, 32, 0, stream>>>(*a, out_ids, out_vals, max_n, n_out);
+  return (int)cudaGetLastError();
+}
+extern "C" int fps_ring_entry_bytes(int stride) {
+  int b = (int)sizeof(Entry) + 4 * stride;
+  return (b + 15) / 16 * 16;
+}
+extern "C" int fps_ring_bytes(int capacity, int stride) {
+  return (int)sizeof(RingHdr) + capacity * fps_ring_entry_bytes(stride);
+}

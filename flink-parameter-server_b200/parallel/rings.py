@@ -1,0 +1,208 @@
+"""Device message tier: peer-memory rings + persistent server kernel + credit-counter client.
+
+See ops/csrc/fps_rings.cu.  ``RingFabric`` lays the rings out in one symmetric-heap allocation
+per rank; ``DeviceMessageServer`` runs the persistent ``fps_server_loop`` kernel for one shard;
+``DeviceRingClient`` is the worker-side ``ParameterServerClient`` equivalent working on id tensors,
+with the pull limiter implemented as a device-resident credit counter + FIFO spill queue.
+
+While a server kernel is resident never call ``torch.cuda.synchronize()`` (device-wide sync waits
+for the persistent kernel); synchronise streams / events instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+from ..store.sharded_table import ShardedTable
+from .fabric import SymmetricHeap
+
+RING_MAX_PEERS = 16
+OP_PULL, OP_PUSH = 1, 2
+UPDATE_OPS = {"add": 0, "assign": 1, "max": 2, "min": 3}
+LOCK_MODES = {None: 0, "none": 0, "A": 1, "B": 2}
+ERRORS = {1: "spin limit exceeded (peer not draining its ring)", 2: "push to an unknown id (LockPSLogic)",
+          3: "waiter pool / spill queue exhausted"}
+
+
+class RingSetC(C.Structure):
+    _fields_ = [("base", C.c_void_p * RING_MAX_PEERS), ("n_peers", C.c_int), ("capacity", C.c_int),
+                ("stride", C.c_int), ("entry_bytes", C.c_int)]
+
+
+class ServerArgsC(C.Structure):
+    _fields_ = [("req", RingSetC), ("resp", RingSetC), ("tab", native.ShardTableC), ("self", C.c_int),
+                ("update_op", C.c_int), ("lock_mode", C.c_int), ("lock_state", C.c_void_p),
+                ("lock_mutex", C.c_void_p), ("wait_head", C.c_void_p), ("pool", C.c_void_p),
+                ("pool_next", C.c_void_p), ("free_head", C.c_void_p), ("pool_size", C.c_int),
+                ("touched", C.c_void_p), ("stop", C.c_void_p), ("err", C.c_void_p),
+                ("counters", C.c_void_p)]
+
+
+class ClientArgsC(C.Structure):
+    _fields_ = [("req", RingSetC), ("resp", RingSetC), ("tab", native.ShardTableC), ("st", C.c_void_p),
+                ("spill", C.c_void_p), ("spill_cap", C.c_int), ("self", C.c_int)]
+
+
+class RingFabric:
+    """Request + response rings of every (worker, shard) pair; rank r is worker r and shard r."""
+
+    def __init__(self, stride: int, capacity: int = 1024, group=None, device: Optional[int] = None):
+        assert capacity & (capacity - 1) == 0, "ring capacity must be a power of two"
+        ready = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ready else 1
+        self.rank = dist.get_rank(group) if ready else 0
+        self.stride, self.capacity = int(stride), int(capacity)
+        lib = native.lib()
+        self.entry_bytes = lib.fps_ring_entry_bytes(self.stride)
+        self.ring_bytes = (lib.fps_ring_bytes(self.capacity, self.stride) + 255) // 256 * 256
+        self.heap = SymmetricHeap(2 * self.world * self.ring_bytes, group=group, device=device)
+
+    def _set(self, bases) -> RingSetC:
+        r = RingSetC()
+        for i, b in enumerate(bases):
+            r.base[i] = b
+        r.n_peers, r.capacity, r.stride, r.entry_bytes = self.world, self.capacity, self.stride, self.entry_bytes
+        return r
+
+    # server view: my request rings (local), the workers' response rings for me (peer)
+    def server_sets(self) -> Tuple[RingSetC, RingSetC]:
+        W, me, rb = self.world, self.rank, self.ring_bytes
+        req = self._set([self.heap.local_ptr + w * rb for w in range(W)])
+        resp = self._set([self.heap.peer_ptrs[w] + (W + me) * rb for w in range(W)])
+        return req, resp
+
+    # client view: every shard's request ring for me (peer), my response rings (local)
+    def client_sets(self) -> Tuple[RingSetC, RingSetC]:
+        W, me, rb = self.world, self.rank, self.ring_bytes
+        req = self._set([self.heap.peer_ptrs[s] + me * rb for s in range(W)])
+        resp = self._set([self.heap.local_ptr + (W + s) * rb for s in range(W)])
+        return req, resp
+
+    def close(self):
+        self.heap.close()
+
+
+class DeviceMessageServer:
+    """Persistent server kernel for the local shard of ``table``."""
+
+    def __init__(self, table: ShardedTable, rings: RingFabric, update: str = "add",
+                 lock: Optional[str] = None, pool_size: int = 1 << 16, require_pull_before_push=None):
+        self.table, self.rings = table, rings
+        dev = table.cuda_device
+        rows = table.rows_per_shard
+        self.lock = LOCK_MODES[lock]
+        z = lambda n, dt=torch.int32: torch.zeros(n, dtype=dt, device=dev)
+        self.lock_state, self.lock_mutex = z(rows), z(rows)
+        self.wait_head = torch.full((rows,), -1, dtype=torch.int32, device=dev)
+        self.pool = z(3 * pool_size)
+        self.pool_next, self.free_head = z(1), torch.full((1,), -1, dtype=torch.int32, device=dev)
+        track = self.lock != 0 if require_pull_before_push is None else require_pull_before_push
+        self.touched = z((rows + 31) // 32) if track else None
+        self.stop_flag, self.err = z(1), z(1)
+        self.counters = z(3, torch.int64)
+        a = ServerArgsC()
+        a.req, a.resp = rings.server_sets()
+        a.tab = table.table_c
+        a.self, a.update_op, a.lock_mode = rings.rank, UPDATE_OPS[update], self.lock
+        a.lock_state, a.lock_mutex = self.lock_state.data_ptr(), self.lock_mutex.data_ptr()
+        a.wait_head, a.pool = self.wait_head.data_ptr(), self.pool.data_ptr()
+        a.pool_next, a.free_head, a.pool_size = self.pool_next.data_ptr(), self.free_head.data_ptr(), pool_size
+        a.touched = self.touched.data_ptr() if self.touched is not None else None
+        a.stop, a.err, a.counters = self.stop_flag.data_ptr(), self.err.data_ptr(), self.counters.data_ptr()
+        self.args = a
+        self.stream = torch.cuda.Stream(device=dev)
+        self.ctl = torch.cuda.Stream(device=dev)
+        self.running = False
+
+    def start(self) -> None:
+        torch.cuda.current_stream().synchronize()
+        native._check(native.lib().fps_server_loop_launch(C.byref(self.args), C.c_void_p(self.stream.cuda_stream)),
+                      "server_loop_launch")
+        native._bump()
+        self.running = True
+
+    def stop(self) -> None:
+        if not self.running:
+            return
+        with torch.cuda.stream(self.ctl):
+            self.stop_flag.fill_(1)
+        self.ctl.synchronize()
+        self.stream.synchronize()
+        self.running = False
+        code = int(self._read(self.err)[0])
+        if code:
+            raise RuntimeError(f"device server: {ERRORS.get(code, code)}")
+
+    def _read(self, t: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.stream(self.ctl):
+            out = t.to("cpu", non_blocking=False)
+        return out
+
+    def stats(self) -> dict:
+        c = self._read(self.counters).tolist()
+        return {"pulls": c[0], "pushes": c[1], "answers": c[2]}
+
+
+class DeviceRingClient:
+    """Worker-side client: ``pull(ids)`` / ``push(ids, deltas)`` / ``collect()`` on id tensors with a
+    device credit counter of ``pull_limit`` unanswered pulls."""
+
+    def __init__(self, table: ShardedTable, rings: RingFabric, pull_limit: int = 1600,
+                 spill_capacity: int = 1 << 16):
+        dev = table.cuda_device
+        self.dev, self.stride = dev, rings.stride
+        self.state = torch.zeros(10, dtype=torch.int32, device=dev)
+        self.state[0] = pull_limit
+        self.state[1] = pull_limit
+        self.spill = torch.zeros(spill_capacity, dtype=torch.int64, device=dev)
+        a = ClientArgsC()
+        a.req, a.resp = rings.client_sets()
+        a.tab = table.table_c
+        a.st, a.spill, a.spill_cap, a.self = self.state.data_ptr(), self.spill.data_ptr(), spill_capacity, rings.rank
+        self.args = a
+        self.stream = torch.cuda.Stream(device=dev)
+        self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.current_stream().synchronize()
+
+    def _issue(self, ids: torch.Tensor, deltas: Optional[torch.Tensor], op: int) -> None:
+        ids = ids.to(self.dev, torch.int64).contiguous()
+        with torch.cuda.stream(self.stream):
+            native._check(native.lib().fps_client_issue(
+                C.byref(self.args), C.c_void_p(ids.data_ptr()),
+                C.c_void_p(deltas.data_ptr() if deltas is not None else None), int(ids.numel()), op,
+                C.c_void_p(self.stream.cuda_stream)), "client_issue")
+            native._bump()
+        self.stream.synchronize()
+
+    def pull(self, ids: torch.Tensor) -> None:
+        self._issue(ids, None, OP_PULL)
+
+    def push(self, ids: torch.Tensor, deltas: torch.Tensor) -> None:
+        d = torch.zeros((ids.numel(), self.stride), dtype=torch.float32, device=self.dev)
+        d[:, : deltas.shape[1]] = deltas
+        self._issue(ids, d, OP_PUSH)
+
+    def collect(self, max_n: int = 1024) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Consume up to ``max_n`` answers (= ``onPullRecv`` calls); releases credits and issues queued pulls."""
+        ids = torch.empty(max_n, dtype=torch.int64, device=self.dev)
+        vals = torch.empty((max_n, self.stride), dtype=torch.float32, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            native._check(native.lib().fps_client_collect(
+                C.byref(self.args), C.c_void_p(ids.data_ptr()), C.c_void_p(vals.data_ptr()), int(max_n),
+                C.c_void_p(self.n_out.data_ptr()), C.c_void_p(self.stream.cuda_stream)), "client_collect")
+            native._bump()
+            n = int(self.n_out.to("cpu")[0])
+        return ids[:n], vals[:n]
+
+    def counters(self) -> dict:
+        with torch.cuda.stream(self.stream):
+            s = self.state.to("cpu").tolist()
+        code = s[9]
+        if code:
+            raise RuntimeError(f"device client: {ERRORS.get(code, code)}")
+        return {"credits": s[0], "limit": s[1], "issued": s[2] | (s[3] << 32),
+                "queued": (s[6] | (s[7] << 32)) - (s[4] | (s[5] << 32))}
