@@ -225,7 +225,7 @@ def main():
             "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "impl": a.impl, "kernel": a.kernel or os.environ.get("FPS_MF_KERNEL", "tma"),
+            "impl": a.impl, "kernel": a.kernel or os.environ.get("FPS_MF_KERNEL", "reg"),
             "config": {"model": "online SGD MF 10Mx1M k=64 (psOnlineMF)", "users": a.users,
                        "items": a.items, "factors": a.factors,
                        "global_batch": a.batch * world, "per_gpu_batch": a.batch,
