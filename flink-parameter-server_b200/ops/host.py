@@ -1,0 +1,78 @@
+"""ctypes bindings for ``libfps_host.so`` (native host runtime: partitioner/packer, key interner)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List
+
+import numpy as np
+import torch
+
+from . import build as _build
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not _build.HOST_LIB.exists():
+                    _build.build_host()
+                l = C.CDLL(str(_build.HOST_LIB))
+                l.fps_interner_new.restype = C.c_void_p
+                l.fps_interner_size.restype = C.c_int64
+                l.fps_interner_size.argtypes = [C.c_void_p]
+                l.fps_interner_free.argtypes = [C.c_void_p]
+                _lib = l
+    return _lib
+
+
+def partition_pack(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, workers: int,
+                   pin: bool = True, threads: int = 0) -> List[torch.Tensor]:
+    """Bucket a block of ratings by ``user % workers`` into per-worker packed64 tensors (pinned)."""
+    u = users.to(torch.int32).contiguous(); i = items.to(torch.int32).contiguous()
+    r = ratings.to(torch.float32).contiguous()
+    n = u.numel()
+    counts = (C.c_int64 * workers)()
+    lib().fps_host_count_by_worker(C.c_void_p(u.data_ptr()), C.c_int64(n), workers, counts)
+    outs = [torch.empty(int(counts[w]), dtype=torch.int64, pin_memory=pin and torch.cuda.is_available())
+            for w in range(workers)]
+    ptrs = (C.c_void_p * workers)(*[o.data_ptr() for o in outs])
+    rc = lib().fps_host_partition_pack(C.c_void_p(u.data_ptr()), C.c_void_p(i.data_ptr()),
+                                       C.c_void_p(r.data_ptr()), C.c_int64(n), workers, ptrs,
+                                       threads or min(8, os.cpu_count() or 1))
+    if rc != 0:
+        raise ValueError("ids exceed the packed64 record range (user < 2^26, item < 2^22)")
+    return outs
+
+
+class NativeInterner:
+    """64-bit key -> dense slot, C++ hash map (thread safe)."""
+
+    def __init__(self):
+        self._p = C.c_void_p(lib().fps_interner_new())
+
+    def map(self, keys, insert: bool = True) -> np.ndarray:
+        k = np.ascontiguousarray(np.asarray(keys, dtype=np.int64))
+        out = np.empty(k.shape[0], dtype=np.int32)
+        lib().fps_interner_map(self._p, k.ctypes.data_as(C.c_void_p), C.c_int64(k.shape[0]),
+                               out.ctypes.data_as(C.c_void_p), int(insert))
+        return out
+
+    def __len__(self) -> int:
+        return int(lib().fps_interner_size(self._p))
+
+    def keys(self) -> np.ndarray:
+        out = np.empty(len(self), dtype=np.int64)
+        lib().fps_interner_keys(self._p, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def __del__(self):
+        try:
+            lib().fps_interner_free(self._p)
+        except Exception:
+            pass
