@@ -191,3 +191,48 @@ def test_packed64_records_equal_array_inputs(dev):
     with pytest.raises(ValueError):
         native.pack_ratings(torch.tensor([1 << 26]), torch.tensor([0]), torch.tensor([1.0]))
     m1.close(); m2.close()
+
+
+def test_generic_device_tier_batched_worker_logic(dev):
+    """A user BatchedWorkerLogic on the device engine: word-count style pull -> push(+1) -> output."""
+    from fps_b200.api import BatchedWorkerLogic
+    from fps_b200.runtime.device_engine import transform_device
+    from fps_b200.store.sharded_table import ShardedTable
+
+    class CountLogic(BatchedWorkerLogic):
+        def onRecvBatch(self, batch, ps):
+            ps.pull(batch)
+
+        def onPullRecvBatch(self, ids, values, ps):
+            ps.output((int(ids.numel()), float(values.sum())))
+            ps.push(ids, torch.ones(ids.numel(), 4, device=ids.device))
+
+    table = ShardedTable(1000, 4, init="zeros", track_touched=True)
+    batches = [torch.randint(0, 50, (200,), device=dev) for _ in range(6)]
+    out = transform_device(batches, CountLogic(), table, pull_limit=64, worker_streams=2)
+    counts = torch.bincount(torch.cat(batches), minlength=1000).float()
+    model = dict((i, v) for i, v in out.ps_outputs())
+    assert set(model) == set(torch.cat(batches).unique().tolist())
+    for i, v in model.items():
+        assert torch.allclose(v, torch.full((4,), counts[i].item()))
+    assert sum(n for n, _ in out.worker_outputs()) == 1200
+    assert max(n for n, _ in out.worker_outputs()) <= 64        # pull limiter chunks
+    table.close()
+
+
+def test_ps_online_mf_device_backend_through_reference_api(dev):
+    import random
+
+    import numpy as np
+
+    from fps_b200.models.mf.common import Rating
+    from fps_b200.models.mf.offline import psOfflineMF
+
+    r = random.Random(47)
+    ratings = [Rating(r.randrange(20), r.randrange(15), r.random()) for _ in range(100)]
+    out = psOfflineMF(ratings, numFactors=15, rangeMin=0.0, rangeMax=0.25, learningRate=0.05, iterations=150,
+                      backend="device", seed=3, plain_residual=True, batch_size=64)
+    users = dict(out.worker_outputs()); items = dict(out.ps_outputs())
+    rmse = (sum((x.rating - float(np.dot(users[x.user], items[x.item]))) ** 2 for x in ratings) / len(ratings)) ** 0.5
+    assert rmse <= 0.5, rmse
+    out.model.close()
