@@ -80,12 +80,16 @@ struct MfArgs {
   int user_div;               // workerParallelism: local slot = user / user_div
   int user_shift;             // log2(user_div) if power of two, else -1
   float lr;
-  int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual
+  int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual r - u.v;
+                              // 2: logistic r - sigmoid(u.v) (skip-gram negative sampling)
   int format;                 // 0: users/items/ratings arrays; 1: packed64 records in `users`
                               //    (user:26 | item:22 | rating fp16:16) -- 8 B/update over PCIe
   float* stats;               // [0] += sum (r-u.v)^2, [1] += #updates
   int* nan_flag;              // set to 1 if a non-finite update was produced
   ShardTable item_tab;
+  ShardTable user_tab;        // used when user_sharded != 0: the "user" rows also live on the PS
+  int user_sharded;           //   (word2vec: input vectors and output vectors are both PS tables)
+  int pad2_;
 };
 
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(256, MINB)
           item = (IdT)neg;
         }
       }
-      up[r] = a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
+      up[r] = a.user_sharded ? fps_row_t<IdT>(a.user_tab, user)
+                             : a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
       vp[r] = fps_row_t<IdT>(a.item_tab, item);
 #pragma unroll
       for (int c = 0; c < VPL; ++c) {
@@ -169,7 +174,9 @@ __global__ void __launch_bounds__(256, MINB)
              u[r][c].w * v[r][c].w;
       d = fps_group_sum<LPR>(d);
       const float resid = rt[r] - d;
-      const float e = (a.err_mode == 0) ? 1.f / (1.f + __expf(-resid)) : resid;
+      const float e = (a.err_mode == 0)   ? 1.f / (1.f + __expf(-resid))
+                      : (a.err_mode == 1) ? resid
+                                          : rt[r] - 1.f / (1.f + __expf(-d));
       const float g = a.lr * e;
       if (ok[r]) {
         if (!(fabsf(g) <= 3.0e38f)) bad = true;  // NaN/Inf guard (Vector.scala:78-80)

@@ -36,6 +36,9 @@ struct MfArgs {  // must match fps_core.cu
   float* stats;
   int* nan_flag;
   ShardTable item_tab;
+  ShardTable user_tab;
+  int user_sharded;
+  int pad2_;
 };
 
 #define TILE_ROWS 32
@@ -167,7 +170,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           if (neg == (long long)item[p]) neg = (neg + 1 + (long long)(s.z % 7u)) % a.num_items;
           item[p] = (IdT)neg;
         }
-        float* up = a.user_table + fps_user_slot<IdT>(user[p], a.user_div, a.user_shift) * (size_t)stride;
+        float* up = a.user_sharded
+                        ? fps_row_t<IdT>(a.user_tab, user[p])
+                        : a.user_table + fps_user_slot<IdT>(user[p], a.user_div, a.user_shift) * (size_t)stride;
         float* vp = fps_row_t<IdT>(a.item_tab, item[p]);
         mbar_wait(&empty[stage], phase ^ 1u);  // slot free (credit available)
         RowMeta m;
@@ -215,7 +220,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         }
         d = fps_group_sum<LPR>(d);
         const float resid = m.rating - d;
-        const float e = (a.err_mode == 0) ? 1.f / (1.f + __expf(-resid)) : resid;
+        const float e = (a.err_mode == 0)   ? 1.f / (1.f + __expf(-resid))
+                        : (a.err_mode == 1) ? resid
+                                            : m.rating - 1.f / (1.f + __expf(-d));
         const float g = a.lr * e;
         if (m.valid) {
           if (!(fabsf(g) <= 3.0e38f)) bad = true;

@@ -62,6 +62,9 @@ class MfArgsC(C.Structure):
         ("stats", C.c_void_p),
         ("nan_flag", C.c_void_p),
         ("item_tab", ShardTableC),
+        ("user_tab", ShardTableC),
+        ("user_sharded", C.c_int),
+        ("pad2_", C.c_int),
     ]
 
 
@@ -219,7 +222,7 @@ def init_rows(rows: torch.Tensor, dim: int, shard: int, num_shards: int, mode: i
 
 
 def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor,
-                 user_table: torch.Tensor, user_div: int, item_tab: ShardTableC, lr: float,
+                 user_table, user_div: int, item_tab: ShardTableC, lr: float,
                  err_mode: int = 0, neg_rate: int = 0, num_items: int = 0, seed: int = 0,
                  step: int = 0, stats: Optional[torch.Tensor] = None,
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
@@ -231,7 +234,9 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     256-byte rows, kept for large rows (measurements: profiles/mf_fused_history.md).
     ``items=None`` means ``users`` holds packed64 records (see :func:`pack_ratings`)."""
     _req(users, "users")
-    _req(user_table, "user_table", torch.float32)
+    user_sharded = isinstance(user_table, ShardTableC)
+    if not user_sharded:
+        _req(user_table, "user_table", torch.float32)
     packed = items is None
     if packed:
         if users.dtype != torch.int64:
@@ -240,7 +245,7 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
         _req(items, "items"); _req(ratings, "ratings", torch.float32)
         if users.dtype != items.dtype:
             raise TypeError("users and items must share an integer dtype")
-    if user_table.shape[1] != item_tab.stride:
+    if (user_table.stride if user_sharded else user_table.shape[1]) != item_tab.stride:
         raise ValueError("user table stride must equal item table stride")
     a = MfArgsC()
     a.users = users.data_ptr()
@@ -249,7 +254,11 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.format = 1 if packed else 0
     a.n_pos = users.numel(); a.neg_rate = int(neg_rate); a.num_items = int(max(num_items, 1))
     a.seed = seed & (2**64 - 1); a.step = int(step)
-    a.user_table = user_table.data_ptr(); a.user_div = int(user_div)
+    if user_sharded:
+        a.user_table = None; a.user_tab = user_table; a.user_sharded = 1
+    else:
+        a.user_table = user_table.data_ptr(); a.user_sharded = 0
+    a.user_div = int(user_div)
     a.user_shift = log2_or_neg(int(user_div))
     a.lr = float(lr); a.err_mode = int(err_mode)
     a.stats = stats.data_ptr() if stats is not None else None
