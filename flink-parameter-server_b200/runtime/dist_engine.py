@@ -1,0 +1,112 @@
+"""Multi-process host tier: the same ``WorkerLogic`` / ``ParameterServerLogic`` callbacks with one
+process per rank, messages exchanged through ``torch.distributed`` (gloo on CPU, NCCL works too).
+
+Rank r hosts worker r and PS shard r (``workerParallelism == psParallelism == world_size``).  The
+job advances in rounds; in every round each rank
+
+  1. feeds up to ``records_per_round`` local input records to ``workerLogic.onRecv``,
+  2. exchanges the produced worker->PS messages (bucketed by ``paramPartitioner``), lets its PS shard
+     handle them (``onPullRecv`` / ``onPushRecv``),
+  3. exchanges the PS->worker answers (bucketed by ``wInPartition``) and delivers them
+     (``onPullRecv``), whose pushes / pulls travel in the next round.
+
+Message lists keep their order, so delivery is FIFO per (producer, consumer) pair like Flink's
+channels.  The job ends when every rank is out of input and a full round moved no message (the
+distributed form of the local engine's quiescence detection; the reference uses a timeout,
+FPS:480).  This is the plumbing path of BASELINE.json config 1 (CPU, world_size=2).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Iterable, List, Optional
+
+import torch.distributed as dist
+
+from ..api import Left, ParameterServer, ParameterServerClient, Right, RuntimeContext
+from ..protocol.senders import (SimplePSReceiver, SimplePSSender, SimpleWorkerReceiver,
+                                SimpleWorkerSender)
+from .stream import ResultStream
+from .transform import default_param_partitioner, default_worker_partitioner
+
+
+def _exchange(buckets: List[List[Any]], group) -> List[Any]:
+    """buckets[d] = messages for rank d.  Returns the messages addressed to this rank, ordered by
+    source rank then send order."""
+    world = dist.get_world_size(group)
+    gathered: List[Optional[List[List[Any]]]] = [None] * world
+    dist.all_gather_object(gathered, buckets, group=group)
+    me = dist.get_rank(group)
+    out: List[Any] = []
+    for src in range(world):
+        out.extend(gathered[src][me])
+    return out
+
+
+def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
+                          paramPartitioner: Optional[Callable[[Any], int]] = None,
+                          wInPartition: Optional[Callable[[Any], int]] = None, group=None,
+                          records_per_round: int = 256, gather_results: bool = True) -> ResultStream:
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    part = paramPartitioner or default_param_partitioner(world)
+    wpart = wInPartition or default_worker_partitioner(world)
+    w_send, w_recv = SimpleWorkerSender(), SimpleWorkerReceiver()
+    p_send, p_recv = SimplePSSender(), SimplePSReceiver()
+    results: List[Any] = []
+    to_ps: List[List[Any]] = [[] for _ in range(world)]
+    to_worker: List[List[Any]] = [[] for _ in range(world)]
+
+    class Client(ParameterServerClient):
+        def pull(self, id):
+            w_send.onPull(id, lambda m: to_ps[int(part(m)) % world].append(m), rank)
+
+        def push(self, id, deltaUpdate):
+            w_send.onPush(id, deltaUpdate, lambda m: to_ps[int(part(m)) % world].append(m), rank)
+
+        def output(self, out):
+            results.append(Left(out))
+
+    class Server(ParameterServer):
+        def answerPull(self, id, value, workerPartitionIndex):
+            def collect(m):
+                d = int(wpart(m))
+                if not 0 <= d < world:
+                    raise RuntimeError("Pull answer key should be the partition ID itself!")
+                to_worker[d].append(m)
+
+            p_send.onPullAnswer(id, value, workerPartitionIndex, collect)
+
+        def output(self, out):
+            results.append(Right(out))
+
+    client, server = Client(), Server()
+    workerLogic.open()
+    psLogic.open({}, RuntimeContext(rank, world))
+    it = iter(local_data)
+    exhausted = False
+    while True:
+        fed = 0
+        while not exhausted and fed < records_per_round:
+            try:
+                workerLogic.onRecv(next(it), client)
+                fed += 1
+            except StopIteration:
+                exhausted = True
+        out_ps, to_ps[:] = list(to_ps), [[] for _ in range(world)]
+        n_moved = sum(len(b) for b in out_ps)
+        for m in _exchange(out_ps, group):
+            p_recv.onWorkerMsg(m, lambda id, widx: psLogic.onPullRecv(id, widx, server),
+                               lambda id, delta: psLogic.onPushRecv(id, delta, server))
+        out_w, to_worker[:] = list(to_worker), [[] for _ in range(world)]
+        n_moved += sum(len(b) for b in out_w)
+        for m in _exchange(out_w, group):
+            w_recv.onPullAnswerRecv(m, lambda a: workerLogic.onPullRecv(a.paramId, a.param, client))
+        status = [None] * world
+        dist.all_gather_object(status, (exhausted, n_moved, sum(len(b) for b in to_ps)), group=group)
+        if all(s[0] and s[1] == 0 and s[2] == 0 for s in status):
+            break
+    workerLogic.close()
+    psLogic.close(server)
+    if gather_results:
+        allr = [None] * world
+        dist.all_gather_object(allr, results, group=group)
+        results = [x for part_ in allr for x in part_]
+    return ResultStream(results)
