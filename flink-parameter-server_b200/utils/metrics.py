@@ -1,0 +1,87 @@
+"""Quality metrics + lightweight counters (the reference only has these inside its tests:
+T/matrix/factorization/sink/nDCGSink.scala:192-272, T/test/utils/PassiveAggressive*ModelEvaluation.scala)."""
+from __future__ import annotations
+
+import math
+import threading
+from collections import defaultdict
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+
+def rmse(pairs: Iterable[Tuple[float, float]]) -> float:
+    se, n = 0.0, 0
+    for pred, target in pairs:
+        se += (pred - target) ** 2
+        n += 1
+    return math.sqrt(se / max(n, 1))
+
+
+def accuracy(pairs: Iterable[Tuple[object, object]]) -> float:
+    ok, n = 0, 0
+    for pred, target in pairs:
+        ok += int(pred == target)
+        n += 1
+    return ok / max(n, 1)
+
+
+def dcg_at_k(ranked_items: Sequence[int], relevant_item: int, k: int) -> float:
+    """Single relevant item (the next item the user interacts with), like the nDCG sink."""
+    for rank, it in enumerate(ranked_items[:k]):
+        if it == relevant_item:
+            return 1.0 / math.log2(rank + 2)
+    return 0.0
+
+
+class NDCGSink:
+    """Prequential evaluation of top-K lists: every ``(user, item, time, topK)`` record scores the list
+    that was produced BEFORE the model saw the rating; aggregates nDCG@K and hit-rate per period
+    (``period_of(time)``, e.g. days)."""
+
+    def __init__(self, K: int, period_of=lambda t: 0):
+        self.K, self.period_of = K, period_of
+        self.sum_ndcg: Dict[int, float] = defaultdict(float)
+        self.hits: Dict[int, int] = defaultdict(int)
+        self.count: Dict[int, int] = defaultdict(int)
+
+    def invoke(self, record) -> None:
+        _user, item, ts, topk = record
+        p = self.period_of(ts)
+        items = [i for _, i in topk]
+        g = dcg_at_k(items, item, self.K)
+        self.sum_ndcg[p] += g
+        self.hits[p] += int(g > 0)
+        self.count[p] += 1
+
+    def result(self) -> List[Tuple[int, float, float, int]]:
+        """``[(period, nDCG@K, hitRate, events)]`` sorted by period."""
+        return [(p, self.sum_ndcg[p] / self.count[p], self.hits[p] / self.count[p], self.count[p])
+                for p in sorted(self.count)]
+
+    def to_csv(self, path: str) -> None:
+        with open(path, "w") as f:
+            f.write("period,ndcg,hit_rate,events\n")
+            for row in self.result():
+                f.write(",".join(str(x) for x in row) + "\n")
+
+
+class Counters:
+    """Thread-safe named counters / gauges (pulls, pushes, credit stalls, ring occupancy, ...)."""
+
+    def __init__(self):
+        self._v: Dict[str, float] = defaultdict(float)
+        self._lock = threading.Lock()
+
+    def inc(self, name: str, by: float = 1) -> None:
+        with self._lock:
+            self._v[name] += by
+
+    def set(self, name: str, value: float) -> None:
+        with self._lock:
+            self._v[name] = value
+
+    def snapshot(self) -> Dict[str, float]:
+        with self._lock:
+            return dict(self._v)
+
+
+GLOBAL = Counters()
