@@ -91,3 +91,38 @@ def merge_partial_topk(scores: torch.Tensor, items: torch.Tensor, K: int,
         scores = torch.where(seen_mask, torch.full_like(scores, -3.0e38), scores)
     top = torch.topk(scores, min(K, scores.shape[1]), dim=1)
     return top.values, torch.gather(items, 1, top.indices)
+
+
+class DistributedTopK:
+    """Top-K serving across ranks (capability of ``psTopKGenerator``): user vectors on the PS
+    (``user_table``), every rank holds a partition of the items (``local_items`` with their global ids
+    ``local_item_ids``); every query is answered by every rank with its local top-``workerK`` (the
+    reference broadcasts each rating to all workers, PSTopKGenerator.scala:78-89) and the partial lists
+    are merged (E9: gather + K-way merge = ``CollectTopKFromEachWorker``)."""
+
+    def __init__(self, user_table: ShardedTable, local_items: torch.Tensor, local_item_ids: torch.Tensor,
+                 group=None):
+        import torch.distributed as dist
+
+        self.users, self.group = user_table, group
+        self.local = DeviceTopK(local_items)
+        self.item_ids = local_item_ids.to(torch.int64)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def topk(self, query_user_ids: torch.Tensor, K: int, workerK: Optional[int] = None):
+        import torch.distributed as dist
+
+        wk = min(workerK or K, self.local.n_items)
+        sc, rows = self.local.topk(wk, q_ids=query_user_ids, q_table=self.users)
+        gids = self.item_ids[rows]
+        if self.world == 1:
+            return merge_partial_topk(sc, gids, K)
+        if wk < (workerK or K):  # pad so all ranks contribute equally sized lists
+            pad = (workerK or K) - wk
+            sc = torch.nn.functional.pad(sc, (0, pad), value=-3.0e38)
+            gids = torch.nn.functional.pad(gids, (0, pad), value=-1)
+        all_sc = [torch.empty_like(sc) for _ in range(self.world)]
+        all_id = [torch.empty_like(gids) for _ in range(self.world)]
+        dist.all_gather(all_sc, sc.contiguous(), group=self.group)
+        dist.all_gather(all_id, gids.contiguous(), group=self.group)
+        return merge_partial_topk(torch.cat(all_sc, 1), torch.cat(all_id, 1), K)
