@@ -94,7 +94,7 @@ class DevicePassiveAggressive:
         ids = torch.tensor([m[0] for m in model], dtype=torch.int64, device=self.dev)
         vals = torch.tensor(np.array([np.atleast_1d(np.asarray(m[1], dtype=np.float32)) for m in model]),
                             device=self.dev)
-        self.table.push(ids, vals.contiguous())
+        self.table.load(ids, vals.contiguous())
 
     def check_finite(self):
         if int(self.nan_flag.item()):

@@ -340,6 +340,30 @@ __global__ void __launch_bounds__(256)
   if (bad && nan_flag != nullptr) *nan_flag = 1;
 }
 
+// Model load (transformWithModelLoad, FPS:715-908): table[ids[i], :] = values[i, :] (one-sided store).
+template <typename IdT, int LPR>
+__global__ void __launch_bounds__(256)
+    fps_push_assign_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
+                           long long n, const float* __restrict__ vals, int val_stride, int touch) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int nvec = t.stride >> 2;
+  for (long long i = group; i < n; i += n_groups) {
+    float* dst = fps_row_t<IdT>(t, ids[i]);
+    if (touch && lane == 0) fps_touch(t, (long long)ids[i]);
+    for (int q = lane; q < nvec; q += LPR) {
+      const float* d = vals + i * (long long)val_stride + 4 * q;
+      float4 v;
+      v.x = (4 * q + 0 < val_stride) ? d[0] : 0.f;
+      v.y = (4 * q + 1 < val_stride) ? d[1] : 0.f;
+      v.z = (4 * q + 2 < val_stride) ? d[2] : 0.f;
+      v.w = (4 * q + 3 < val_stride) ? d[3] : 0.f;
+      *reinterpret_cast<float4*>(dst + 4 * q) = v;
+    }
+  }
+}
+
 template <typename IdT, int LPR>
 __global__ void __launch_bounds__(256)
     fps_pull_dot_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
@@ -438,6 +462,22 @@ extern "C" int fps_pull_dot(const ShardTable* t, const void* ids, int id_bytes, 
   } else {
     FPS_DISPATCH_LPR(fps_pull_dot_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
                      n, local, local_stride, score)
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                               const float* vals, int val_stride, int touch, int num_sms,
+                               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int lpr = pick_lpr(t->stride >> 2);
+  const int grid = row_grid(n, lpr, num_sms);
+  if (id_bytes == 4) {
+    FPS_DISPATCH_LPR(fps_push_assign_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, vals,
+                     val_stride, touch)
+  } else {
+    FPS_DISPATCH_LPR(fps_push_assign_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
+                     n, vals, val_stride, touch)
   }
   return (int)cudaGetLastError();
 }

@@ -316,6 +316,17 @@ def push_add(tab: ShardTableC, ids: torch.Tensor, delta: torch.Tensor, scale: fl
     _bump()
 
 
+def push_assign(tab: ShardTableC, ids: torch.Tensor, values: torch.Tensor, touch: bool = False) -> None:
+    """table[ids[i]] = values[i] (model load); one-sided vector stores to the owning shard."""
+    _req(ids, "ids"); _req(values, "values", torch.float32)
+    assert values.shape[0] == ids.numel() and values.shape[1] <= tab.stride
+    _check(lib().fps_push_assign(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
+                                 C.c_longlong(ids.numel()), C.c_void_p(values.data_ptr()),
+                                 int(values.shape[1]), int(bool(touch)), sm_count(ids.device.index),
+                                 _stream()), "push_assign")
+    _bump()
+
+
 def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: torch.Tensor) -> None:
     _req(ids, "ids"); _req(local, "local", torch.float32); _req(score, "score", torch.float32)
     assert local.shape[0] == ids.numel() == score.numel()

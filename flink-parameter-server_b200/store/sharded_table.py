@@ -133,8 +133,8 @@ class ShardedTable:
 
     def load(self, ids: torch.Tensor, values: torch.Tensor) -> None:
         """Model load: overwrite rows with given values (any rank may load any id)."""
-        cur = self.pull(ids)
-        self.push(ids, (values.to(torch.float32) - cur).contiguous())
+        native.push_assign(self.table_c, ids, values.to(torch.float32).contiguous(),
+                           touch=self.track_touched)
 
     def barrier(self) -> None:
         self.heap.barrier()

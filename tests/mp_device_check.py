@@ -77,6 +77,39 @@ def main():
     m2.barrier()
     assert m2.stats[1].item() == 50000
     m2.close(); m.close()
+    # ---- message tier across GPUs: rings in peer memory, persistent server on every rank ----------
+    from fps_b200.parallel.rings import DeviceMessageServer, DeviceRingClient, RingFabric
+    import time
+
+    tab = ShardedTable(1000, 8, seed=21, init_range=(0.0, 1.0))
+    ref_all = tab.pull(torch.arange(1000, device=dev)).cpu()
+    rings = RingFabric(tab.stride, capacity=128)
+    server = DeviceMessageServer(tab, rings, update="add")
+    client = DeviceRingClient(tab, rings, pull_limit=16)
+    server.start()
+    dist.barrier()
+    want = torch.arange(rank, 200, 3)                  # ids owned by BOTH shards, 16-credit limiter
+    client.pull(want)
+    got_ids, got_vals, t0 = [], [], time.time()
+    while sum(x.numel() for x in got_ids) < want.numel():
+        i, v = client.collect(64)
+        got_ids.append(i.cpu()); got_vals.append(v.cpu())
+        assert time.time() - t0 < 20, "ring answers did not arrive"
+    gi, gv = torch.cat(got_ids), torch.cat(got_vals)
+    order = torch.argsort(gi)
+    assert torch.equal(gi[order], torch.sort(want).values)
+    torch.testing.assert_close(gv[order][:, :8], ref_all[torch.sort(want).values])
+    client.push(want, torch.ones(want.numel(), 8, device=dev))
+    time.sleep(0.3)
+    dist.barrier()
+    server.stop()
+    dist.barrier()
+    expect = ref_all.clone()
+    for r_ in range(world):
+        expect[torch.arange(r_, 200, 3)] += 1
+    after = tab.pull(torch.arange(1000, device=dev)).cpu()
+    torch.testing.assert_close(after, expect)
+    rings.close(); tab.close()
     dist.barrier()
     if rank == 0:
         print(f"MP_DEVICE_CHECK_OK world={world} fabric={m.items.heap.mode}")
