@@ -80,6 +80,31 @@ class DeviceOnlineMF:
                             max_inflight_rows=self.pull_limit, kernel=self.kernel)
         self.step_no += 1
 
+    def make_graph_step(self, batch_size: int, packed: bool = True):
+        """CUDA-graph a fixed-size micro-batch step for launch-bound streaming (small batches).
+
+        Returns ``(static_inputs, replay)``: copy the next batch into ``static_inputs`` (device
+        tensors) and call ``replay()``; the captured graph contains the stats reset and the fused
+        kernel, so one ``cudaGraphLaunch`` replaces the Python + ctypes launch path."""
+        dev = self.cuda_device
+        if packed:
+            static = (torch.zeros(batch_size, dtype=torch.int64, device=dev),)
+        else:
+            static = (torch.zeros(batch_size, dtype=torch.int32, device=dev),
+                      torch.zeros(batch_size, dtype=torch.int32, device=dev),
+                      torch.zeros(batch_size, dtype=torch.float32, device=dev))
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm up outside capture
+                self.stats.zero_(); self.step(*static)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            self.stats.zero_()
+            self.step(*static)
+        return static, graph.replay
+
     def fit_stream(self, host_batches: Iterable[Sequence[torch.Tensor]],
                    loss_every: int = 1):
         """End-to-end training over pinned host micro-batches ``(users, items, ratings)``.

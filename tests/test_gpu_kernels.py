@@ -236,3 +236,25 @@ def test_ps_online_mf_device_backend_through_reference_api(dev):
     rmse = (sum((x.rating - float(np.dot(users[x.user], items[x.item]))) ** 2 for x in ratings) / len(ratings)) ** 0.5
     assert rmse <= 0.5, rmse
     out.model.close()
+
+
+def test_cuda_graph_step_replays_fused_kernel(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+    from fps_b200.ops import native
+
+    nu, ni, k, b = 5000, 3000, 64, 2048
+    g = torch.Generator().manual_seed(9)
+    m1 = DeviceOnlineMF(nu, ni, k, learning_rate=0.05, seed=5)
+    m2 = DeviceOnlineMF(nu, ni, k, learning_rate=0.05, seed=5)
+    static, replay = m2.make_graph_step(b, packed=True)
+    m2.users.copy_(m1.users); m2.items.local.copy_(m1.items.local)      # undo the warm-up steps
+    for _ in range(3):
+        u = torch.randperm(nu, generator=g)[:b].int(); i = torch.randperm(ni, generator=g)[:b].int()
+        r = torch.rand(b, generator=g).half().float()
+        rec = native.pack_ratings(u, i, r).cuda()
+        m1.step(rec)
+        static[0].copy_(rec); replay()
+    torch.cuda.synchronize()
+    assert torch.equal(m1.users, m2.users) and torch.equal(m1.items.local, m2.items.local)
+    assert m2.stats[1].item() == b
+    m1.close(); m2.close()
