@@ -49,6 +49,9 @@ def parse():
     p.add_argument("--format", default="packed64", choices=["packed64", "arrays"],
                    help="rating record format: packed64 = 8 B/update (user:26|item:22|fp16 rating), "
                         "arrays = int32 user, int32 item, fp32 rating (12 B/update)")
+    p.add_argument("--item-cache", default="auto", choices=["auto", "on", "off"],
+                   help="worker-side item cache + per-step delta merge (default: on when N > 1)")
+    p.add_argument("--sync-every", type=int, default=1, help="item-cache: merge every k micro-batches")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()
@@ -138,8 +141,10 @@ def main():
         from fps_b200.parallel.nccl_baseline import NcclOnlineMF as Model
     else:
         Model = DeviceOnlineMF
+    cache = {"auto": None, "on": True, "off": False}[a.item_cache]
     model = Model(a.users, a.items, a.factors, learning_rate=a.lr, pull_limit=a.pull_limit,
-                  seed=1234, err_mode=ERR_SIGMOID, kernel=a.kernel)
+                  seed=1234, err_mode=ERR_SIGMOID, kernel=a.kernel, item_cache=cache,
+                  sync_every=a.sync_every)
 
     # ---- synthetic ratings: users owned by this worker (user % W == rank), uniform items -------
     g = torch.Generator().manual_seed(1000 + rank)
@@ -175,6 +180,8 @@ def main():
     e0.record()
     for s in range(a.steps):
         model.step(*devb[(a.warmup + s) % len(devb)])
+    if hasattr(model, "flush"):
+        model.flush()          # item-cache mode: the timed region includes every delta merge
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -234,6 +241,8 @@ def main():
                        "l2": "inputs larger than L2: 2.8 GB of factor tables accessed at random, "
                              f"{len(host)} distinct {h2d >> 20} MiB rating batches cycled",
                        "pull_limit": a.pull_limit or "hardware max rows in flight",
+                       "item_cache": bool(getattr(model, "item_cache", False)),
+                       "sync_every": a.sync_every,
                        "record_format": a.format if a.impl == "fps_b200" else "arrays",
                        "update_rule": "reference parity e=sigmoid(r-u.v), fp32 (reference: fp64 JVM)"},
             "clocks": clocks,

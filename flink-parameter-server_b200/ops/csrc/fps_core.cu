@@ -89,7 +89,8 @@ struct MfArgs {
   ShardTable item_tab;
   ShardTable user_tab;        // used when user_sharded != 0: the "user" rows also live on the PS
   int user_sharded;           //   (word2vec: input vectors and output vectors are both PS tables)
-  int pad2_;
+  int use_push_tab;           // != 0: item deltas are pushed into push_tab instead of item_tab
+  ShardTable push_tab;        //   (worker-side delta staging of the item-cache mode, see fps_cache_sync)
 };
 
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256, MINB)
     float4 u[R][VPL], v[R][VPL];
     float* up[R];
     float* vp[R];
+    float* pp[R];
     float rt[R];
     bool ok[R];
 #pragma unroll
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(256, MINB)
       up[r] = a.user_sharded ? fps_row_t<IdT>(a.user_tab, user)
                              : a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
       vp[r] = fps_row_t<IdT>(a.item_tab, item);
+      pp[r] = a.use_push_tab ? fps_row_t<IdT>(a.push_tab, item) : vp[r];
 #pragma unroll
       for (int c = 0; c < VPL; ++c) {
         const int q = lane + c * LPR;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(256, MINB)
             float4 du = make_float4(g * v[r][c].x, g * v[r][c].y, g * v[r][c].z, g * v[r][c].w);
             float4 dv = make_float4(g * u[r][c].x, g * u[r][c].y, g * u[r][c].z, g * u[r][c].w);
             fps_red_add4(up[r] + 4 * q, du);   // worker-local user update
-            fps_red_add4(vp[r] + 4 * q, dv);   // the PUSH, fused with paramUpdate
+            fps_red_add4(pp[r] + 4 * q, dv);   // the PUSH, fused with paramUpdate
           }
         }
       }
@@ -478,6 +481,53 @@ extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_byte
   } else {
     FPS_DISPATCH_LPR(fps_push_assign_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
                      n, vals, val_stride, touch)
+  }
+  return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------
+// Item-cache mode (sender-side combining, the aggregated form of the reference's batching senders
+// M/common/CombinationLogic.scala): workers run the fused step against a LOCAL replica of the item
+// table and stage their deltas locally; this kernel merges one staging buffer into the master shards
+// (one REDG per touched row instead of one per update) and refreshes the replica from the masters.
+// Each row crosses NVLink at most once per direction per sync, as a streaming transfer.
+// ----------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+    fps_cache_sync_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
+                          float* __restrict__ stage, long long n_rows) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int stride = master.stride;
+  const int nvec = stride >> 2;
+  for (long long i = group; i < n_rows; i += n_groups) {
+    float* m = fps_row(master, i);
+    float* c = cache + i * (long long)stride;
+    float* d = stage + i * (long long)stride;
+    for (int q = lane; q < nvec; q += LPR) {
+      const float4 dv = *reinterpret_cast<const float4*>(d + 4 * q);
+      if (dv.x != 0.f || dv.y != 0.f || dv.z != 0.f || dv.w != 0.f) {
+        fps_red_add4(m + 4 * q, dv);                                   // merged PUSH
+        *reinterpret_cast<float4*>(d + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      *reinterpret_cast<float4*>(c + 4 * q) = fps_ld_row4(m + 4 * q);  // refresh (PULL)
+    }
+  }
+}
+
+extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* stage, long long n_rows,
+                              int num_sms, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  const int lpr = pick_lpr(master->stride >> 2);
+  const int grid = row_grid(n_rows, lpr, num_sms);
+  switch (lpr) {
+    case 1: fps_cache_sync_kernel<1><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
+    case 2: fps_cache_sync_kernel<2><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
+    case 4: fps_cache_sync_kernel<4><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
+    case 8: fps_cache_sync_kernel<8><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
+    case 16: fps_cache_sync_kernel<16><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
+    default: fps_cache_sync_kernel<32><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
   }
   return (int)cudaGetLastError();
 }

@@ -38,7 +38,8 @@ struct MfArgs {  // must match fps_core.cu
   ShardTable item_tab;
   ShardTable user_tab;
   int user_sharded;
-  int pad2_;
+  int use_push_tab;
+  ShardTable push_tab;
 };
 
 #define TILE_ROWS 32

@@ -64,7 +64,8 @@ class MfArgsC(C.Structure):
         ("item_tab", ShardTableC),
         ("user_tab", ShardTableC),
         ("user_sharded", C.c_int),
-        ("pad2_", C.c_int),
+        ("use_push_tab", C.c_int),
+        ("push_tab", ShardTableC),
     ]
 
 
@@ -226,7 +227,7 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  err_mode: int = 0, neg_rate: int = 0, num_items: int = 0, seed: int = 0,
                  step: int = 0, stats: Optional[torch.Tensor] = None,
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
-                 kernel: Optional[str] = None) -> None:
+                 kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -264,8 +265,10 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.stats = stats.data_ptr() if stats is not None else None
     a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
     a.item_tab = item_tab
+    if push_tab is not None:
+        a.push_tab = push_tab; a.use_push_tab = 1
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
-    if packed:
+    if packed or push_tab is not None:
         variant = "reg"
     rv = os.environ.get("FPS_MF_REG_VARIANT")
     if rv is not None:
@@ -324,6 +327,26 @@ def push_assign(tab: ShardTableC, ids: torch.Tensor, values: torch.Tensor, touch
                                  C.c_longlong(ids.numel()), C.c_void_p(values.data_ptr()),
                                  int(values.shape[1]), int(bool(touch)), sm_count(ids.device.index),
                                  _stream()), "push_assign")
+    _bump()
+
+
+def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
+    """A single-shard ShardTable over a local ``[rows, stride]`` tensor (row index == id)."""
+    _req(t, "table", torch.float32)
+    tc = ShardTableC()
+    tc.base[0] = t.data_ptr()
+    tc.rows_per_shard = t.shape[0]; tc.div = t.shape[0]; tc.num_shards = 1
+    tc.dim = int(dim); tc.stride = t.shape[1]; tc.mode = PART_HASH; tc.shard_shift = 0
+    return tc
+
+
+def cache_sync(master: ShardTableC, cache: torch.Tensor, stage: torch.Tensor) -> None:
+    """Merge a local delta staging buffer into the master shards and refresh the local replica."""
+    _req(cache, "cache", torch.float32); _req(stage, "stage", torch.float32)
+    assert cache.shape == stage.shape and cache.shape[1] == master.stride
+    _check(lib().fps_cache_sync(C.byref(master), C.c_void_p(cache.data_ptr()),
+                                C.c_void_p(stage.data_ptr()), C.c_longlong(cache.shape[0]),
+                                sm_count(cache.device.index), _stream()), "cache_sync")
     _bump()
 
 

@@ -34,7 +34,7 @@ class NcclOnlineMF:
     def __init__(self, num_users: int, num_items: int, num_factors: int = 10,
                  range_min: float = -0.01, range_max: float = 0.01, learning_rate: float = 0.01,
                  negative_sample_rate: int = 0, pull_limit: int = 0, group=None, seed: int = 0,
-                 err_mode: int = ERR_SIGMOID, device: Optional[torch.device] = None, **_):
+                 err_mode: int = ERR_SIGMOID, device: Optional[torch.device] = None, **_ignored):
         ready = dist.is_available() and dist.is_initialized()
         self.group = group
         self.world = dist.get_world_size(group) if ready else 1
