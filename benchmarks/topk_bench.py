@@ -5,6 +5,8 @@ torch (cuBLAS fp32 matmul + torch.topk) on the same data."""
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see fps_b200/__init__.py
 import sys
 
 import torch

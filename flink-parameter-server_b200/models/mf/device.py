@@ -215,7 +215,10 @@ class DeviceOnlineMF:
         return ids[sel], self.users[sel, : self.k].clone()
 
     def item_vectors(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.items.dump_local()
+        """All item vectors of the local shard (the fused kernel does not maintain the touched bitmap:
+        with Philox lazy-init every id has a well-defined value whether or not it was pulled)."""
+        self.flush()
+        return self.items.dump_local(only_touched=False)
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:

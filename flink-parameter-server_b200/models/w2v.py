@@ -46,6 +46,12 @@ class DeviceSkipGram:
         va, vb = self.w_in.pull(a), self.w_in.pull(b)
         return torch.nn.functional.cosine_similarity(va, vb)
 
+    def score(self, centers: torch.Tensor, contexts: torch.Tensor) -> torch.Tensor:
+        """sigmoid(W_in[center] . W_out[context]) -- the model's co-occurrence probability."""
+        u = self.w_in.pull(centers)
+        return torch.sigmoid(self.w_out.pull_dot(contexts, torch.nn.functional.pad(
+            u, (0, self.w_out.stride - u.shape[1])).contiguous()))
+
     def check_finite(self):
         if int(self.nan_flag.item()):
             raise FloatingPointError("non-finite skip-gram update")

@@ -385,3 +385,14 @@ extern "C" int fps_ring_entry_bytes(int stride) {
 extern "C" int fps_ring_bytes(int capacity, int stride) {
   return (int)sizeof(RingHdr) + capacity * fps_ring_entry_bytes(stride);
 }
+
+// CUDA loads kernels lazily; the first launch of a not-yet-loaded kernel needs a context-wide
+// synchronisation and therefore DEADLOCKS while a persistent kernel is resident.  Force-load every
+// kernel of this file before the server starts.
+extern "C" int fps_rings_preload() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, fps_server_loop_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fps_client_issue_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fps_client_collect_kernel);
+  return (int)e;
+}

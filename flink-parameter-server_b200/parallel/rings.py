@@ -119,6 +119,16 @@ class DeviceMessageServer:
         self.running = False
 
     def start(self) -> None:
+        # CUDA loads kernels lazily and the first launch of an unloaded kernel synchronises the
+        # context -- a deadlock once the persistent kernel is resident.  Load everything used while
+        # the server runs *now*: our ring kernels, and the torch kernels of stop()/stats()/clients.
+        native._check(native.lib().fps_rings_preload(), "rings_preload")
+        with torch.cuda.stream(self.ctl):
+            self.stop_flag.fill_(0)
+            _ = self.counters.to("cpu"); _ = self.err.to("cpu")
+            w = torch.zeros(4, dtype=torch.int64, device=self.stop_flag.device)
+            _ = (w + 1).to(torch.float32).contiguous(); _ = torch.empty(4, device=w.device).zero_()
+        self.ctl.synchronize()
         torch.cuda.current_stream().synchronize()
         native._check(native.lib().fps_server_loop_launch(C.byref(self.args), C.c_void_p(self.stream.cuda_stream)),
                       "server_loop_launch")
@@ -166,6 +176,14 @@ class DeviceRingClient:
         self.args = a
         self.stream = torch.cuda.Stream(device=dev)
         self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        # pre-load the torch kernels this client launches later (see DeviceMessageServer.start)
+        with torch.cuda.stream(self.stream):
+            _ = torch.arange(4).to(dev, torch.int64).contiguous()
+            d = torch.zeros((2, self.stride), dtype=torch.float32, device=dev)
+            d[:, :1] = torch.ones(2, 1, device=dev)
+            _ = torch.empty(4, dtype=torch.int64, device=dev)[:2].to("cpu")
+            _ = self.state.to("cpu"); _ = self.n_out.to("cpu")
+        self.stream.synchronize()
         torch.cuda.current_stream().synchronize()
 
     def _issue(self, ids: torch.Tensor, deltas: Optional[torch.Tensor], op: int) -> None:

@@ -6,6 +6,8 @@ Checks the symmetric-heap fabric (every rank sees every shard), one-sided pull /
 shards, and the fused MF step against a single-process fp32 PyTorch reference.
 """
 import os
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see fps_b200/__init__.py
 import sys
 
 import torch
