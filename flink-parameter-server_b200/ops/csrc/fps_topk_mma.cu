@@ -125,7 +125,7 @@ __device__ __forceinline__ void tk_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <typename IdT>
+template <typename IdT, int MODE>
 __global__ void __launch_bounds__(TK_THREADS, 1)
     fps_topk_mma_kernel(const __grid_constant__ CUtensorMap item_map,
                         const __grid_constant__ TopkArgs a) {
@@ -244,12 +244,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
     const int r = ew * 32 + lane;               // row inside the 128-row query block
     const int row = row0 + r;
     const bool row_ok = row < a.n_queries;
-    const float th = (a.mode == 2 && row_ok) ? a.theta[row] : 0.f;
+    const float th = (MODE == 2 && row_ok) ? a.theta[row] : 0.f;
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const uint32_t aph = (uint32_t)((i >> 1) & 1);
       const int tile = tile_begin + i;
       const int item0 = tile * TK_N;
+      const bool full_tile = item0 + TK_N <= a.n_items;   // no per-element bound check needed
       tk_mbar_wait(&tfull[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float tmax = -3.0e38f;
@@ -257,17 +258,27 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
       for (int c0 = 0; c0 < TK_N; c0 += 32) {
         uint32_t v[32];
         tk_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TK_N + c0), v);
-        if (row_ok) {
+        if (!row_ok) continue;
+        if (MODE == 1) {
+          if (full_tile) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int item = item0 + c0 + j;
-            const float sc = __uint_as_float(v[j]);
-            if (item < a.n_items) {
-              if (a.mode == 0) {
-                a.out_scores[(size_t)row * a.out_ld + item] = sc;
-              } else if (a.mode == 1) {
-                tmax = fmaxf(tmax, sc);
-              } else if (sc >= th) {
+            for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (item0 + c0 + j < a.n_items) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+          }
+        } else if (MODE == 2) {
+          // candidates are rare: first a branch-free "any >= theta" test over the 32 columns
+          float cmax = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+          if (cmax >= th) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int item = item0 + c0 + j;
+              const float sc = __uint_as_float(v[j]);
+              if (sc >= th && item < a.n_items) {
                 const int slot = atomicAdd(a.cand_count + row, 1);
                 if (slot < a.cand_cap) {
                   a.cand_score[(size_t)row * a.cand_cap + slot] = sc;
@@ -276,9 +287,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
               }
             }
           }
+        } else {
+          float* out = a.out_scores + (size_t)row * a.out_ld + item0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_tile || item0 + c0 + j < a.n_items) out[j] = __uint_as_float(v[j]);
         }
       }
-      if (a.mode == 1 && row_ok) a.tile_max[(size_t)row * a.n_tiles + tile] = tmax;
+      if (MODE == 1 && row_ok) a.tile_max[(size_t)row * a.n_tiles + tile] = tmax;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) tk_mbar_arrive(&tempty[acc]);
@@ -327,7 +343,7 @@ extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, in
   if (r != CUDA_SUCCESS) return -1005;
   a.n_tiles = (a.n_items + TK_N - 1) / TK_N;
   const int qblocks = (a.n_queries + TK_M - 1) / TK_M;
-  int splits = (2 * num_sms + qblocks - 1) / qblocks;  // ~2 CTAs per SM worth of work items
+  int splits = num_sms / qblocks;  // one wave of CTAs (1 CTA/SM: smem bound), no tail wave
   if (splits > a.n_tiles) splits = a.n_tiles;
   if (splits < 1) splits = 1;
   a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
@@ -338,17 +354,19 @@ extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, in
   if (stages < 2) return -1003;
   a.n_stages = stages;
   const size_t smem = blk * (1 + stages) + 16 * 8 + 16 + 1024;
-  cudaError_t e;
+  const int grid = qblocks * a.n_splits;
+#define TK_LAUNCH(IDT, MODE)                                                                       \
+  do {                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(fps_topk_mma_kernel<IDT, MODE>,                           \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e != cudaSuccess) return (int)e;                                                           \
+    fps_topk_mma_kernel<IDT, MODE><<<grid, TK_THREADS, smem, stream>>>(map, a);                    \
+  } while (0)
   if (id_bytes == 8) {
-    e = cudaFuncSetAttribute(fps_topk_mma_kernel<long long>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    fps_topk_mma_kernel<long long><<<qblocks * a.n_splits, TK_THREADS, smem, stream>>>(map, a);
+    if (a.mode == 0) TK_LAUNCH(long long, 0); else if (a.mode == 1) TK_LAUNCH(long long, 1); else TK_LAUNCH(long long, 2);
   } else {
-    e = cudaFuncSetAttribute(fps_topk_mma_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    fps_topk_mma_kernel<int><<<qblocks * a.n_splits, TK_THREADS, smem, stream>>>(map, a);
+    if (a.mode == 0) TK_LAUNCH(int, 0); else if (a.mode == 1) TK_LAUNCH(int, 1); else TK_LAUNCH(int, 2);
   }
+#undef TK_LAUNCH
   return (int)cudaGetLastError();
 }
