@@ -2,8 +2,8 @@
 config 3: "wide-&-deep CTR (1B-slot embedding shard) async SGD, pull-limiter=64").
 
 The sparse side (hashed categorical features -> embedding rows) is the parameter server: rows are
-pulled with the one-sided gather kernel in credit-sized chunks (``pull_limit`` rows in flight per
-chunk), the dense tower (a small MLP, replicated per worker) runs with torch autograd, and the
+pulled with the one-sided gather kernel under the device-side pull limiter (at most ``pull_limit``
+row pulls in flight), the dense tower (a small MLP, replicated per worker) runs with torch autograd, and the
 embedding gradients are pushed back with ``red.add`` (asynchronous SGD: no barrier between workers).
 The "wide" linear term is an extra 1-wide column of the same rows.  Not part of the reference's
 algorithm suite; it exercises the generic tensor tier at embedding-table scale
@@ -34,12 +34,8 @@ class DeviceWideAndDeep:
         self.opt = torch.optim.SGD(self.mlp.parameters(), lr=learning_rate)
 
     def _pull(self, ids: torch.Tensor) -> torch.Tensor:
-        flat = ids.reshape(-1)
-        out = torch.empty((flat.numel(), self.emb_dim + 1), dtype=torch.float32, device=self.dev)
-        lim = self.pull_limit if self.pull_limit > 0 else flat.numel()
-        for a in range(0, flat.numel(), lim):           # at most pull_limit rows in flight per chunk
-            self.table.pull(flat[a:a + lim], out[a:a + lim])
-        return out
+        # device-side pull limiter: one launch, at most `pull_limit` row pulls in flight
+        return self.table.pull(ids.reshape(-1).contiguous(), pull_limit=self.pull_limit)
 
     def step(self, ids: torch.Tensor, labels: torch.Tensor) -> float:
         """ids: [B, fields] hashed feature slots, labels: [B] in {0,1}.  Returns the batch log-loss."""

@@ -421,12 +421,21 @@ static inline int row_grid(long long n, int lpr, int num_sms) {
     default: KERNEL<IDT, 32><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__); break;                  \
   }
 
+// max_inflight_rows > 0 is the device-side pull limiter (WL:196-250) of the generic tier: the grid is
+// capped so that at most that many row pulls are in flight (one per resident lane-group).
+static inline int limit_grid(int grid, int lpr, int max_inflight_rows) {
+  if (max_inflight_rows <= 0) return grid;
+  int cap = max_inflight_rows / (256 / lpr);
+  if (cap < 1) cap = 1;
+  return grid < cap ? grid : cap;
+}
+
 extern "C" int fps_pull_gather(const ShardTable* t, const void* ids, int id_bytes, long long n,
                                float* out, int out_stride, int touch, int num_sms,
-                               cudaStream_t stream) {
+                               int max_inflight_rows, cudaStream_t stream) {
   if (n <= 0) return 0;
   const int lpr = pick_lpr(t->stride >> 2);
-  const int grid = row_grid(n, lpr, num_sms);
+  const int grid = limit_grid(row_grid(n, lpr, num_sms), lpr, max_inflight_rows);
   if (id_bytes == 4) {
     FPS_DISPATCH_LPR(fps_pull_gather_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, out,
                      out_stride, touch)

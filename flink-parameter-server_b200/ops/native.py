@@ -297,13 +297,14 @@ def pack_ratings(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     return (users.to(torch.int64) << 38) | (items.to(torch.int64) << 16) | r16
 
 
-def pull_gather(tab: ShardTableC, ids: torch.Tensor, out: torch.Tensor, touch: bool = False) -> None:
+def pull_gather(tab: ShardTableC, ids: torch.Tensor, out: torch.Tensor, touch: bool = False,
+                max_inflight_rows: int = 0) -> None:
     _req(ids, "ids"); _req(out, "out", torch.float32)
     assert out.shape[0] == ids.numel() and out.shape[1] <= tab.stride
     _check(lib().fps_pull_gather(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
                                  C.c_longlong(ids.numel()), C.c_void_p(out.data_ptr()),
                                  int(out.shape[1]), int(bool(touch)), sm_count(ids.device.index),
-                                 _stream()), "pull_gather")
+                                 int(max_inflight_rows), _stream()), "pull_gather")
     _bump()
 
 

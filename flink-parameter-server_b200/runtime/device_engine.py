@@ -35,7 +35,7 @@ class DeviceParameterServerClient(BatchedParameterServerClient):
 
     def pull_now(self, ids: torch.Tensor) -> torch.Tensor:
         self.pulled_rows += ids.numel()
-        return self.table.pull(ids)
+        return self.table.pull(ids, pull_limit=self.pull_limit)
 
     def pull(self, ids: torch.Tensor) -> None:
         lim = self.pull_limit if self.pull_limit > 0 else ids.numel()

@@ -93,11 +93,14 @@ class ShardedTable:
         return slots + self.rank * self.div
 
     # -- generic tensor tier: batched pull / push ---------------------------------------------
-    def pull(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """values[i] = table[ids[i]] -- one-sided gather from the owning shards (K1)."""
+    def pull(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None,
+             pull_limit: int = 0) -> torch.Tensor:
+        """values[i] = table[ids[i]] -- one-sided gather from the owning shards (K1).
+        ``pull_limit`` > 0 bounds the row pulls in flight on the device (the pull limiter)."""
         if out is None:
             out = torch.empty((ids.numel(), self.dim), dtype=torch.float32, device=ids.device)
-        native.pull_gather(self.table_c, ids, out, touch=self.track_touched)
+        native.pull_gather(self.table_c, ids, out, touch=self.track_touched,
+                           max_inflight_rows=pull_limit)
         return out
 
     def push(self, ids: torch.Tensor, deltas: torch.Tensor, scale: float = 1.0) -> None:
