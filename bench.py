@@ -53,7 +53,7 @@ def parse():
                         "arrays = int32 user, int32 item, fp32 rating (12 B/update)")
     p.add_argument("--item-cache", default="auto", choices=["auto", "on", "off"],
                    help="worker-side item cache + per-step delta merge (default: on when N > 1)")
-    p.add_argument("--sync-every", type=int, default=1, help="item-cache: merge every k micro-batches")
+    p.add_argument("--sync-every", type=int, default=2, help="item-cache: merge every k micro-batches")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()
@@ -132,6 +132,8 @@ def main():
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)          # NCCL prints its version banner on stdout; rank 0 must print ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -253,7 +255,9 @@ def main():
                     "last_step_mse": (last[0] / last[1]) if last[1] else None},
             "gpu_launches": launches,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -55,8 +55,8 @@ def main():
         k = torch.arange(rows, device=dev)
         owner = (rank + 1 + k % (world - 1)) % world if world > 1 else torch.zeros_like(k)
         ids = ((k // max(1, world - 1)) * world + owner).to(torch.int64)
-        buf = torch.empty((rows, dim), dtype=torch.float32, device=dev)
-        delta = torch.ones((rows, dim), dtype=torch.float32, device=dev)
+        buf = torch.empty((rows, table.stride), dtype=torch.float32, device=dev)
+        delta = torch.ones((rows, table.stride), dtype=torch.float32, device=dev)
         nbytes = rows * dim * 4
         t_pull = timed(lambda: table.pull(ids, buf))
         t_push = timed(lambda: table.push(ids, delta))

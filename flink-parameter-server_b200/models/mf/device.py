@@ -39,7 +39,7 @@ class DeviceOnlineMF:
                  group=None, seed: int = 0, err_mode: int = ERR_SIGMOID,
                  device: Optional[int] = None, track_touched: bool = False,
                  kernel: Optional[str] = None, item_cache: Optional[bool] = None,
-                 sync_every: int = 1):
+                 sync_every: int = 2):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -69,10 +69,10 @@ class DeviceOnlineMF:
             self.stats = torch.zeros(2, dtype=torch.float32, device=self.cuda_device)
             self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.cuda_device)
         # ---- item-cache mode (sender-side combining) --------------------------------------------
-        # Workers train against a local replica of the item table, stage deltas locally (double
-        # buffered) and a streaming sync kernel merges them into the master shards / refreshes the
-        # replica on a side stream: every row crosses NVLink once per sync instead of once per update.
-        # Staleness is bounded by `sync_every` micro-batches (still asynchronous: no barriers).
+        # The worker trains a local replica of the item table (pulls and pushes stay in local HBM)
+        # and every `sync_every` micro-batches merges (replica - base) into the master shards and
+        # refreshes the replica: every row crosses NVLink once per sync instead of once per update.
+        # Still asynchronous (no barriers); staleness is bounded by `sync_every` micro-batches.
         if item_cache is None:
             item_cache = self.world > 1 and os.environ.get("FPS_ITEM_CACHE", "1") != "0"
         self.item_cache = bool(item_cache)
@@ -84,59 +84,31 @@ class DeviceOnlineMF:
                 self.items.barrier()
                 all_ids = torch.arange(n_pad, device=self.cuda_device, dtype=torch.int64)
                 native.pull_gather(self.items.table_c, all_ids, self.cache)
-                self.stage = [torch.zeros_like(self.cache), torch.zeros_like(self.cache)]
+                self.base = self.cache.clone()
                 self.cache_c = native.local_table(self.cache, self.k)
-                self.stage_c = [native.local_table(s_, self.k) for s_ in self.stage]
-                self.sync_stream = torch.cuda.Stream(device=self.cuda_device)
-                self._sync_done = [None, None]
-                self._buf = 0
                 self._since_sync = 0
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
-    def _launch_sync(self, buf: int) -> None:
-        cur = torch.cuda.current_stream(self.cuda_device)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self.sync_stream.wait_event(ev)
-        with torch.cuda.stream(self.sync_stream):
-            native.cache_sync(self.items.table_c, self.cache, self.stage[buf])
-            done = torch.cuda.Event()
-            done.record(self.sync_stream)
-        self._sync_done[buf] = done
-
     def flush(self) -> None:
-        """Item-cache mode: merge every staged delta and make the current stream wait for it."""
-        if not self.item_cache:
-            return
-        cur = torch.cuda.current_stream(self.cuda_device)
-        if self._since_sync > 0:
-            self._launch_sync(self._buf)
-            self._buf ^= 1
+        """Item-cache mode: merge the replica's pending changes into the master shards now."""
+        if self.item_cache and self._since_sync > 0:
+            native.cache_sync(self.items.table_c, self.cache, self.base)
             self._since_sync = 0
-        for ev in self._sync_done:
-            if ev is not None:
-                cur.wait_event(ev)
 
     def step(self, users: torch.Tensor, items: Optional[torch.Tensor] = None,
              ratings: Optional[torch.Tensor] = None) -> None:
         """Process one micro-batch of ratings whose users belong to this worker (async SGD).
         ``step(packed)`` with a single int64 tensor takes packed64 records (``native.pack_ratings``)."""
         if self.item_cache:
-            cur = torch.cuda.current_stream(self.cuda_device)
-            if self._since_sync == 0 and self._sync_done[self._buf] is not None:
-                cur.wait_event(self._sync_done[self._buf])      # staging buffer free again
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.cache_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=self.neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
-                                max_inflight_rows=self.pull_limit, kernel="reg",
-                                push_tab=self.stage_c[self._buf])
+                                max_inflight_rows=self.pull_limit, kernel="reg")
             self._since_sync += 1
             if self._since_sync >= self.sync_every:
-                self._launch_sync(self._buf)
-                self._buf ^= 1
-                self._since_sync = 0
+                self.flush()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=self.neg,

@@ -397,6 +397,69 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Wide rows (dim > 1024 floats, e.g. the 16K..1M-float vectors of the bandwidth sweep): one lane-group
+// per row would leave the GPU idle, so the work item is (row, 4 KiB segment) and every lane keeps
+// 8 independent 16-byte transfers in flight.  OP 0: pull (peer -> out), 1: push-add, 2: assign.
+#define FPS_WIDE_SEG_VEC 256   // float4 per segment
+template <typename IdT, int OP>
+__global__ void __launch_bounds__(256)
+    fps_wide_rows_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids, long long n,
+                         float* __restrict__ buf, int buf_stride, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = t.stride >> 2;
+  const int n_seg = (nvec + FPS_WIDE_SEG_VEC - 1) / FPS_WIDE_SEG_VEC;
+  const long long total = n * n_seg;
+  for (long long w = warp; w < total; w += n_warps) {
+    const long long i = w / n_seg;
+    const int seg = (int)(w - i * n_seg);
+    float* row = fps_row_t<IdT>(t, ids[i]);
+    float* b = buf + i * (long long)buf_stride;
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = seg * FPS_WIDE_SEG_VEC + k * 32 + lane;
+      if (q < nvec && 4 * q + 3 < buf_stride) {
+        v[k] = (OP == 0) ? fps_ld_row4(row + 4 * q) : *reinterpret_cast<const float4*>(b + 4 * q);
+      } else {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = seg * FPS_WIDE_SEG_VEC + k * 32 + lane;
+      if (q < nvec && 4 * q + 3 < buf_stride) {
+        if (OP == 0) {
+          *reinterpret_cast<float4*>(b + 4 * q) = v[k];
+        } else if (OP == 1) {
+          fps_red_add4(row + 4 * q, make_float4(v[k].x * scale, v[k].y * scale, v[k].z * scale, v[k].w * scale));
+        } else {
+          *reinterpret_cast<float4*>(row + 4 * q) = v[k];
+        }
+      }
+    }
+  }
+}
+
+template <int OP>
+static int launch_wide(const ShardTable* t, const void* ids, int id_bytes, long long n, float* buf,
+                       int buf_stride, float scale, int num_sms, cudaStream_t stream) {
+  const int nvec = t->stride >> 2;
+  const long long total = n * ((nvec + FPS_WIDE_SEG_VEC - 1) / FPS_WIDE_SEG_VEC);
+  long long blocks = (total + 7) / 8;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  if (id_bytes == 4)
+    fps_wide_rows_kernel<int, OP><<<(int)blocks, 256, 0, stream>>>(*t, (const int*)ids, n, buf, buf_stride, scale);
+  else
+    fps_wide_rows_kernel<long long, OP><<<(int)blocks, 256, 0, stream>>>(*t, (const long long*)ids, n, buf, buf_stride, scale);
+  return (int)cudaGetLastError();
+}
+static inline bool use_wide(const ShardTable* t, int buf_stride, int touch) {
+  return (t->stride >> 2) > 256 && (buf_stride & 3) == 0 && buf_stride == t->stride && !touch;
+}
+
 static inline int pick_lpr(int nvec) {
   int l = 1;
   while (l < nvec && l < 32) l <<= 1;
@@ -434,6 +497,8 @@ extern "C" int fps_pull_gather(const ShardTable* t, const void* ids, int id_byte
                                float* out, int out_stride, int touch, int num_sms,
                                int max_inflight_rows, cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (use_wide(t, out_stride, touch) && max_inflight_rows <= 0)
+    return launch_wide<0>(t, ids, id_bytes, n, out, out_stride, 1.f, num_sms, stream);
   const int lpr = pick_lpr(t->stride >> 2);
   const int grid = limit_grid(row_grid(n, lpr, num_sms), lpr, max_inflight_rows);
   if (id_bytes == 4) {
@@ -450,6 +515,8 @@ extern "C" int fps_push_add(const ShardTable* t, const void* ids, int id_bytes, 
                             const float* delta, int delta_stride, float scale, int touch,
                             int* nan_flag, int num_sms, cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (use_wide(t, delta_stride, touch))  // wide rows: no per-element NaN scan (bandwidth path)
+    return launch_wide<1>(t, ids, id_bytes, n, const_cast<float*>(delta), delta_stride, scale, num_sms, stream);
   const int lpr = pick_lpr(t->stride >> 2);
   const int grid = row_grid(n, lpr, num_sms);
   if (id_bytes == 4) {
@@ -475,6 +542,96 @@ extern "C" int fps_pull_dot(const ShardTable* t, const void* ids, int id_bytes, 
     FPS_DISPATCH_LPR(fps_pull_dot_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
                      n, local, local_stride, score)
   }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                               const float* vals, int val_stride, int touch, int num_sms,
+                               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int lpr = pick_lpr(t->stride >> 2);
+  const int grid = row_grid(n, lpr, num_sms);
+  if (id_bytes == 4) {
+    FPS_DISPATCH_LPR(fps_push_assign_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, vals,
+                     val_stride, touch)
+  } else {
+    FPS_DISPATCH_LPR(fps_push_assign_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
+                     n, vals, val_stride, touch)
+  }
+  return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------
+// Item-cache mode (sender-side combining -- the aggregated form of the reference's batching senders,
+// M/common/CombinationLogic.scala): a worker trains a LOCAL replica of the item table with the fused
+// kernel (pulls and pushes are local), and every `sync_every` micro-batches merges what it changed:
+//   phase A (fps_cache_push_delta): delta = replica - base; one REDG per changed 16-byte chunk into
+//            the master shard (owner's HBM over NVLink) -- one transfer per row per sync instead of
+//            one per update;
+//   phase B (fps_cache_refresh):    replica = base = master row (streaming peer reads).
+// The kernel boundary between A and B guarantees the worker's own reductions are visible to its
+// refresh; other workers' deltas that land later are picked up at the next sync (asynchronous,
+// staleness bounded by `sync_every` micro-batches).
+// ----------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+    fps_cache_push_delta_kernel(const __grid_constant__ ShardTable master,
+                                const float* __restrict__ cache, const float* __restrict__ base,
+                                long long n_rows) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int stride = master.stride;
+  const int nvec = stride >> 2;
+  for (long long i = group; i < n_rows; i += n_groups) {
+    float* m = fps_row(master, i);
+    for (int q = lane; q < nvec; q += LPR) {
+      const float4 c = *reinterpret_cast<const float4*>(cache + i * (long long)stride + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(base + i * (long long)stride + 4 * q);
+      const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
+      if (d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f) fps_red_add4(m + 4 * q, d);
+    }
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+    fps_cache_refresh_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
+                             float* __restrict__ base, long long n_rows) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int stride = master.stride;
+  const int nvec = stride >> 2;
+  for (long long i = group; i < n_rows; i += n_groups) {
+    const float* m = fps_row(master, i);
+    for (int q = lane; q < nvec; q += LPR) {
+      const float4 v = fps_ld_row4(m + 4 * q);
+      *reinterpret_cast<float4*>(cache + i * (long long)stride + 4 * q) = v;
+      *reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q) = v;
+    }
+  }
+}
+
+#define FPS_SYNC_DISPATCH(KERNEL, ...)                                         \
+  switch (lpr) {                                                               \
+    case 1: KERNEL<1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+    case 2: KERNEL<2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+    case 4: KERNEL<4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+    case 8: KERNEL<8><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
+    case 16: KERNEL<16><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;         \
+    default: KERNEL<32><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;         \
+  }
+
+extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* base, long long n_rows,
+                              int num_sms, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  const int lpr = pick_lpr(master->stride >> 2);
+  const int grid = row_grid(n_rows, lpr, num_sms);
+  FPS_SYNC_DISPATCH(fps_cache_push_delta_kernel, *master, cache, base, n_rows)
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  FPS_SYNC_DISPATCH(fps_cache_refresh_kernel, *master, cache, base, n_rows)
   return (int)cudaGetLastError();
 }
 

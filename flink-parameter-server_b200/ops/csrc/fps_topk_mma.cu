@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < TK_N; c0 += 32) {
         uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
         tk_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TK_N + c0), v);
-        if (!row_ok) continue;
+        if (row_ok) {
         if (MODE == 1) {
           if (full_tile) {
 #pragma unroll
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
           for (int j = 0; j < 32; ++j)
             if (full_tile || item0 + c0 + j < a.n_items) out[j] = __uint_as_float(v[j]);
         }
+        }  // row_ok
       }
       if (MODE == 1 && row_ok) a.tile_max[(size_t)row * a.n_tiles + tile] = tmax;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

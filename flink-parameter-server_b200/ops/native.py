@@ -341,14 +341,14 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
     return tc
 
 
-def cache_sync(master: ShardTableC, cache: torch.Tensor, stage: torch.Tensor) -> None:
-    """Merge a local delta staging buffer into the master shards and refresh the local replica."""
-    _req(cache, "cache", torch.float32); _req(stage, "stage", torch.float32)
-    assert cache.shape == stage.shape and cache.shape[1] == master.stride
+def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor) -> None:
+    """Merge (replica - base) into the master shards, then refresh replica and base (2 launches)."""
+    _req(cache, "cache", torch.float32); _req(base, "base", torch.float32)
+    assert cache.shape == base.shape and cache.shape[1] == master.stride
     _check(lib().fps_cache_sync(C.byref(master), C.c_void_p(cache.data_ptr()),
-                                C.c_void_p(stage.data_ptr()), C.c_longlong(cache.shape[0]),
+                                C.c_void_p(base.data_ptr()), C.c_longlong(cache.shape[0]),
                                 sm_count(cache.device.index), _stream()), "cache_sync")
-    _bump()
+    _bump(2)
 
 
 def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: torch.Tensor) -> None:

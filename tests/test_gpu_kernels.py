@@ -258,3 +258,21 @@ def test_cuda_graph_step_replays_fused_kernel(dev):
     assert torch.equal(m1.users, m2.users) and torch.equal(m1.items.local, m2.items.local)
     assert m2.stats[1].item() == b
     m1.close(); m2.close()
+
+
+def test_wide_rows_pull_push(dev):
+    """dim > 1024 floats takes the (row, 4 KiB segment) kernel."""
+    from fps_b200.store.sharded_table import ShardedTable
+
+    n, dim = 37, 5000
+    t = ShardedTable(n, dim, seed=3, init_range=(-1.0, 1.0))
+    ref = t.local[:, :dim].clone()
+    ids = torch.randint(0, n, (50,), device=dev)
+    got = torch.empty((50, t.stride), device=dev)
+    from fps_b200.ops import native
+    native.pull_gather(t.table_c, ids, got)
+    torch.testing.assert_close(got[:, :dim], ref[ids], rtol=0, atol=0)
+    delta = torch.randn(50, t.stride, device=dev)
+    native.push_add(t.table_c, ids, delta, scale=0.5)
+    torch.testing.assert_close(t.local[:, :dim], ref.index_add_(0, ids, 0.5 * delta[:, :dim]), rtol=1e-5, atol=1e-5)
+    t.close()
