@@ -122,6 +122,20 @@ class DeviceSketch:
         keys = [self.interner.keys[i] for i in ids[top.indices].cpu().tolist()]
         return list(zip(top.values.cpu().tolist(), keys))
 
+    def query(self, word: str, K: int) -> List[Tuple[float, int]]:
+        """Scatter the query to every shard, gather the local top-K lists and merge them (E8 + E9:
+        the predict jobs' push-broadcast and parallelism-1 merge sink).  Every rank must call it with
+        the same word; all ranks need the same interning (feed them the same key stream or share the
+        dictionary)."""
+        import torch.distributed as dist
+
+        local = self.query_local(word, K)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.table.group) == 1:
+            return merge_topk([local], K)
+        parts = [None] * dist.get_world_size(self.table.group)
+        dist.all_gather_object(parts, local, group=self.table.group)
+        return merge_topk(parts, K)
+
     def close(self):
         self.table.close()
 
