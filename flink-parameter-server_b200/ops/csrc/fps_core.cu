@@ -634,66 +634,3 @@ extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* bas
   FPS_SYNC_DISPATCH(fps_cache_refresh_kernel, *master, cache, base, n_rows)
   return (int)cudaGetLastError();
 }
-
-extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_bytes, long long n,
-                               const float* vals, int val_stride, int touch, int num_sms,
-                               cudaStream_t stream) {
-  if (n <= 0) return 0;
-  const int lpr = pick_lpr(t->stride >> 2);
-  const int grid = row_grid(n, lpr, num_sms);
-  if (id_bytes == 4) {
-    FPS_DISPATCH_LPR(fps_push_assign_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, vals,
-                     val_stride, touch)
-  } else {
-    FPS_DISPATCH_LPR(fps_push_assign_kernel, long long, lpr, grid, stream, *t, (const long long*)ids,
-                     n, vals, val_stride, touch)
-  }
-  return (int)cudaGetLastError();
-}
-
-// ----------------------------------------------------------------------------------------
-// Item-cache mode (sender-side combining, the aggregated form of the reference's batching senders
-// M/common/CombinationLogic.scala): workers run the fused step against a LOCAL replica of the item
-// table and stage their deltas locally; this kernel merges one staging buffer into the master shards
-// (one REDG per touched row instead of one per update) and refreshes the replica from the masters.
-// Each row crosses NVLink at most once per direction per sync, as a streaming transfer.
-// ----------------------------------------------------------------------------------------
-template <int LPR>
-__global__ void __launch_bounds__(256)
-    fps_cache_sync_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
-                          float* __restrict__ stage, long long n_rows) {
-  const int lane = threadIdx.x & (LPR - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
-  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
-  const int stride = master.stride;
-  const int nvec = stride >> 2;
-  for (long long i = group; i < n_rows; i += n_groups) {
-    float* m = fps_row(master, i);
-    float* c = cache + i * (long long)stride;
-    float* d = stage + i * (long long)stride;
-    for (int q = lane; q < nvec; q += LPR) {
-      const float4 dv = *reinterpret_cast<const float4*>(d + 4 * q);
-      if (dv.x != 0.f || dv.y != 0.f || dv.z != 0.f || dv.w != 0.f) {
-        fps_red_add4(m + 4 * q, dv);                                   // merged PUSH
-        *reinterpret_cast<float4*>(d + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      *reinterpret_cast<float4*>(c + 4 * q) = fps_ld_row4(m + 4 * q);  // refresh (PULL)
-    }
-  }
-}
-
-extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* stage, long long n_rows,
-                              int num_sms, cudaStream_t stream) {
-  if (n_rows <= 0) return 0;
-  const int lpr = pick_lpr(master->stride >> 2);
-  const int grid = row_grid(n_rows, lpr, num_sms);
-  switch (lpr) {
-    case 1: fps_cache_sync_kernel<1><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-    case 2: fps_cache_sync_kernel<2><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-    case 4: fps_cache_sync_kernel<4><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-    case 8: fps_cache_sync_kernel<8><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-    case 16: fps_cache_sync_kernel<16><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-    default: fps_cache_sync_kernel<32><<<grid, 256, 0, stream>>>(*master, cache, stage, n_rows); break;
-  }
-  return (int)cudaGetLastError();
-}

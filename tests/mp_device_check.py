@@ -57,6 +57,9 @@ def main():
     my_users = (torch.randperm(nu // world, generator=gu)[:b] * world + rank).to(dev)
     ratings = torch.rand(b, generator=gu).to(dev)
     V0 = m.items.pull(torch.arange(ni, device=dev))      # whole item table before
+    if m.item_cache:
+        assert torch.equal(m.cache[:ni, :k], V0), "replica != master after init"
+        assert torch.equal(m.base, m.cache), "base != replica after init"
     U0 = m.users[:, :k].clone()
     m.barrier()
     m.step(my_users.int(), my_items.int(), ratings)

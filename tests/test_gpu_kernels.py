@@ -276,3 +276,29 @@ def test_wide_rows_pull_push(dev):
     native.push_add(t.table_c, ids, delta, scale=0.5)
     torch.testing.assert_close(t.local[:, :dim], ref.index_add_(0, ids, 0.5 * delta[:, :dim]), rtol=1e-5, atol=1e-5)
     t.close()
+
+
+def test_item_cache_mode_single_gpu_matches_direct_mode(dev):
+    """Item-cache mode (train a local replica, merge replica-base deltas) must give the direct-mode
+    result for a conflict-free batch, and the master must equal the replica after every sync."""
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    nu, ni, k, b = 6000, 5000, 64, 3000
+    m_direct = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, item_cache=False)
+    m_cache = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, item_cache=True,
+                             sync_every=2)
+    V0 = m_cache.items.local.clone()
+    assert torch.equal(m_cache.cache[:ni], V0[:ni]) and torch.equal(m_cache.base, m_cache.cache)
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        users = torch.randperm(nu, generator=g)[:b].int().cuda()
+        items = torch.randperm(ni, generator=g)[:b].int().cuda()
+        ratings = torch.rand(b, generator=g).cuda()
+        m_direct.step(users, items, ratings); m_cache.step(users, items, ratings)
+    m_cache.flush()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(m_cache.users, m_direct.users, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m_cache.items.local, m_direct.items.local, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m_cache.cache[:ni], m_cache.items.local[:ni], rtol=0, atol=0)
+    assert torch.equal(m_cache.base, m_cache.cache)
+    m_direct.close(); m_cache.close()
