@@ -47,8 +47,11 @@ class DeviceTopK:
         item_rows index the local item table."""
         n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
         Kp = min(K, self.n_items)
-        cap = min(self.n_items, max(Kp * native.TOPK_TILE, native.TOPK_TILE))
-        chunk = max(128, (self.max_batch_bytes // (cap * 8)) // 128 * 128)
+        # worst case K*128 candidates per query (K tiles reach theta); typically a few x K.  Start
+        # with a small buffer and redo pass 2 with the worst-case capacity only if a row overflowed.
+        cap_full = min(self.n_items, max(Kp * native.TOPK_TILE, native.TOPK_TILE))
+        cap_small = min(cap_full, max(1024, 8 * Kp))
+        chunk = max(128, (self.max_batch_bytes // (cap_full * 8)) // 128 * 128)
         outs, outi = [], []
         dev = self.items.device
         for a in range(0, n_q, chunk):
@@ -63,11 +66,14 @@ class DeviceTopK:
                 theta = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
             else:
                 theta = torch.full((n,), -3.0e38, dtype=torch.float32, device=dev)
-            cnt = torch.zeros(n, dtype=torch.int32, device=dev)
-            cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
-            ci = torch.empty((n, cap), dtype=torch.int32, device=dev)
-            native.topk_mma(self.items, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
-                            cand_count=cnt, cand_score=cs, cand_item=ci)
+            for cap in (cap_small, cap_full):
+                cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+                cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
+                ci = torch.empty((n, cap), dtype=torch.int32, device=dev)
+                native.topk_mma(self.items, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
+                                cand_count=cnt, cand_score=cs, cand_item=ci)
+                if cap == cap_full or int(cnt.max().item()) <= cap:
+                    break
             valid = torch.arange(cap, device=dev)[None, :] < cnt.clamp(max=cap)[:, None]
             cs = torch.where(valid, cs, torch.full_like(cs, -3.0e38))
             top = torch.topk(cs, Kp, dim=1)
