@@ -69,10 +69,11 @@ class DeviceOnlineMF:
             self.stats = torch.zeros(2, dtype=torch.float32, device=self.cuda_device)
             self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.cuda_device)
         # ---- item-cache mode (sender-side combining) --------------------------------------------
-        # The worker trains a local replica of the item table (pulls and pushes stay in local HBM)
-        # and every `sync_every` micro-batches merges (replica - base) into the master shards and
-        # refreshes the replica: every row crosses NVLink once per sync instead of once per update.
-        # Still asynchronous (no barriers); staleness is bounded by `sync_every` micro-batches.
+        # The worker trains a local replica of the item table (pulls and pushes stay in local HBM);
+        # every `sync_every` micro-batches a background stream pushes (replica - base) to the master
+        # shards and applies the other workers' contributions (master - base) to the replica: a row
+        # crosses NVLink once per exchange instead of once per update, overlapped with training.
+        # Still asynchronous (no barriers); staleness is bounded by ~2 x `sync_every` micro-batches.
         if item_cache is None:
             item_cache = self.world > 1 and os.environ.get("FPS_ITEM_CACHE", "1") != "0"
         self.item_cache = bool(item_cache)
@@ -87,14 +88,36 @@ class DeviceOnlineMF:
                 self.base = self.cache.clone()
                 self.cache_c = native.local_table(self.cache, self.k)
                 self._since_sync = 0
+                self.sync_stream = torch.cuda.Stream(device=self.cuda_device)
+                self._syncs = []          # completion events of the background delta exchanges
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
-    def flush(self) -> None:
-        """Item-cache mode: merge the replica's pending changes into the master shards now."""
-        if self.item_cache and self._since_sync > 0:
+    def _launch_sync(self) -> None:
+        """Exchange deltas on the background stream (overlaps the next training kernels)."""
+        cur = torch.cuda.current_stream(self.cuda_device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.sync_stream.wait_event(ev)                    # include everything trained so far
+        with torch.cuda.stream(self.sync_stream):
             native.cache_sync(self.items.table_c, self.cache, self.base)
-            self._since_sync = 0
+            done = torch.cuda.Event()
+            done.record(self.sync_stream)
+        self._syncs.append(done)
+        if len(self._syncs) > 2:                           # at most two exchanges outstanding
+            cur.wait_event(self._syncs.pop(0))
+        self._since_sync = 0
+
+    def flush(self) -> None:
+        """Item-cache mode: push every pending local delta to the master shards and wait for it."""
+        if not self.item_cache:
+            return
+        if self._since_sync > 0:
+            self._launch_sync()
+        cur = torch.cuda.current_stream(self.cuda_device)
+        for ev in self._syncs:
+            cur.wait_event(ev)
+        self._syncs = []
 
     def step(self, users: torch.Tensor, items: Optional[torch.Tensor] = None,
              ratings: Optional[torch.Tensor] = None) -> None:
@@ -108,7 +131,7 @@ class DeviceOnlineMF:
                                 max_inflight_rows=self.pull_limit, kernel="reg")
             self._since_sync += 1
             if self._since_sync >= self.sync_every:
-                self.flush()
+                self._launch_sync()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=self.neg,

@@ -564,19 +564,19 @@ extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_byte
 // ----------------------------------------------------------------------------------------
 // Item-cache mode (sender-side combining -- the aggregated form of the reference's batching senders,
 // M/common/CombinationLogic.scala): a worker trains a LOCAL replica of the item table with the fused
-// kernel (pulls and pushes are local), and every `sync_every` micro-batches merges what it changed:
-//   phase A (fps_cache_push_delta): delta = replica - base; one REDG per changed 16-byte chunk into
-//            the master shard (owner's HBM over NVLink) -- one transfer per row per sync instead of
-//            one per update;
-//   phase B (fps_cache_refresh):    replica = base = master row (streaming peer reads).
-// The kernel boundary between A and B guarantees the worker's own reductions are visible to its
-// refresh; other workers' deltas that land later are picked up at the next sync (asynchronous,
-// staleness bounded by `sync_every` micro-batches).
+// kernel (pulls and pushes are local) while a background stream exchanges deltas with the masters:
+//   phase A (push_delta): d = replica - base; REDG d into the master row (owner's HBM over NVLink);
+//            base = the replica value just read.          [one transfer per row per sync, not per update]
+//   phase B (refresh):    f = master - base  (= what OTHER workers contributed since the last sync);
+//            replica += f (local REDG, so concurrent training updates are never lost); base = master.
+// Invariant: replica - base == local updates not yet pushed.  Both phases may run concurrently with
+// the training kernel; the kernel boundary between A and B makes the worker's own reductions visible
+// to its refresh.  Asynchronous (no barriers); staleness is bounded by the sync period.
 // ----------------------------------------------------------------------------------------
 template <int LPR>
 __global__ void __launch_bounds__(256)
     fps_cache_push_delta_kernel(const __grid_constant__ ShardTable master,
-                                const float* __restrict__ cache, const float* __restrict__ base,
+                                const float* __restrict__ cache, float* __restrict__ base,
                                 long long n_rows) {
   const int lane = threadIdx.x & (LPR - 1);
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
@@ -586,10 +586,14 @@ __global__ void __launch_bounds__(256)
   for (long long i = group; i < n_rows; i += n_groups) {
     float* m = fps_row(master, i);
     for (int q = lane; q < nvec; q += LPR) {
-      const float4 c = *reinterpret_cast<const float4*>(cache + i * (long long)stride + 4 * q);
-      const float4 b = *reinterpret_cast<const float4*>(base + i * (long long)stride + 4 * q);
+      const float4 c = fps_ld_row4(cache + i * (long long)stride + 4 * q);
+      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
+      const float4 b = *bp;
       const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
-      if (d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f) fps_red_add4(m + 4 * q, d);
+      if (d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f) {
+        fps_red_add4(m + 4 * q, d);
+        *bp = c;
+      }
     }
   }
 }
@@ -607,8 +611,13 @@ __global__ void __launch_bounds__(256)
     const float* m = fps_row(master, i);
     for (int q = lane; q < nvec; q += LPR) {
       const float4 v = fps_ld_row4(m + 4 * q);
-      *reinterpret_cast<float4*>(cache + i * (long long)stride + 4 * q) = v;
-      *reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q) = v;
+      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
+      const float4 b = *bp;
+      const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+      if (f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f) {
+        fps_red_add4(cache + i * (long long)stride + 4 * q, f);   // foreign contributions
+        *bp = v;
+      }
     }
   }
 }
