@@ -53,7 +53,7 @@ def parse():
                         "arrays = int32 user, int32 item, fp32 rating (12 B/update)")
     p.add_argument("--item-cache", default="auto", choices=["auto", "on", "off"],
                    help="worker-side item cache + per-step delta merge (default: on when N > 1)")
-    p.add_argument("--sync-every", type=int, default=2, help="item-cache: merge every k micro-batches")
+    p.add_argument("--sync-every", type=int, default=4, help="item-cache: merge every k micro-batches")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()

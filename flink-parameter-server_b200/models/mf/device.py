@@ -39,7 +39,7 @@ class DeviceOnlineMF:
                  group=None, seed: int = 0, err_mode: int = ERR_SIGMOID,
                  device: Optional[int] = None, track_touched: bool = False,
                  kernel: Optional[str] = None, item_cache: Optional[bool] = None,
-                 sync_every: int = 2):
+                 sync_every: int = 4):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group

@@ -11,8 +11,7 @@ run () { # n port args...
 show () { python -c "import json,sys;d=json.loads(open('$1').read().strip().splitlines()[-1]);print('$2',d['n_gpus'],'gpus',round(d['value']/1e9,3),'G/s', round(d['ms_per_step'],4),'ms e2e',round(d['e2e']['value']/1e9,3), 'cache',d['config'].get('item_cache'), d['config'].get('sync_every'), d['clocks']['reasons'])" 2>/dev/null || { echo "$2 FAILED"; grep -v "OMP\|\*\*\*" ${1%.json}.err | tail -4; }; }
 run $NG 29617 tests/mp_device_check.py > gpurun_out/p13_mp.log 2>&1; echo "mp rc=$?"; grep -E "OK|rank0.*(Error|assert|Mismatch|Greatest|!=)" gpurun_out/p13_mp.log | head -6
 run $NG 29512 bench.py --gpus $NG --steps 200 --warmup 10 > gpurun_out/b13_n${NG}.json 2> gpurun_out/b13_n${NG}.err; show gpurun_out/b13_n${NG}.json default
-run $NG 29513 bench.py --gpus $NG --steps 200 --warmup 10 --sync-every 4 > gpurun_out/b13_n${NG}_k4.json 2> gpurun_out/b13_n${NG}_k4.err; show gpurun_out/b13_n${NG}_k4.json sync4
-run $NG 29514 bench.py --gpus $NG --steps 200 --warmup 10 --sync-every 1 > gpurun_out/b13_n${NG}_k1.json 2> gpurun_out/b13_n${NG}_k1.err; show gpurun_out/b13_n${NG}_k1.json sync1
+run $NG 29513 bench.py --gpus $NG --steps 200 --warmup 10 --sync-every 2 > gpurun_out/b13_n${NG}_k2.json 2> gpurun_out/b13_n${NG}_k2.err; show gpurun_out/b13_n${NG}_k2.json sync2
 run $NG 29515 bench.py --gpus $NG --steps 100 --warmup 10 --item-cache off > gpurun_out/b13_n${NG}_direct.json 2> gpurun_out/b13_n${NG}_direct.err; show gpurun_out/b13_n${NG}_direct.json direct
 run $NG 29516 bench.py --gpus $NG --steps 20 --warmup 3 --impl nccl > gpurun_out/b13_n${NG}_nccl.json 2> gpurun_out/b13_n${NG}_nccl.err; show gpurun_out/b13_n${NG}_nccl.json nccl
 for n in 4 2; do
