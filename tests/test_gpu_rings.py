@@ -107,3 +107,36 @@ def test_lock_push_before_pull_is_an_error():
     with pytest.raises(RuntimeError):
         server.stop()
     rings.close(); table.close()
+
+
+def test_transform_rings_runs_reference_style_worker_logic_against_device_server():
+    """WorkerLogic callbacks on the host, the store (+ lock logic) in the persistent server kernel."""
+    from fps_b200 import WorkerLogic
+    from fps_b200.runtime.ring_engine import transform_rings
+    from fps_b200.store.sharded_table import ShardedTable
+
+    torch.cuda.set_device(0)
+
+    class PullThenPushOne(WorkerLogic):
+        def onRecv(self, data, ps):
+            ps.pull(data)
+
+        def onPullRecv(self, paramId, paramValue, ps):
+            ps.output((paramId, float(paramValue[0])))
+            ps.push(paramId, torch.ones(4))
+
+    table = ShardedTable(64, 4, init="zeros")
+    data = [i % 16 for i in range(48)]            # every key pulled 3 times, +1 per answer
+    out = transform_rings(data, PullThenPushOne(), table, update="add", lock="A", pull_limit=8)
+    model = {i: v for i, v in out.ps_outputs()}
+    assert sorted(model) == list(range(16))        # lock mode tracks "exists": only pulled keys dumped
+    for i in range(16):
+        assert torch.equal(model[i], torch.full((4,), 3.0))
+    # with per-key locks every worker sees a serialised counter: values 0, 1, 2 per key
+    seen = {}
+    for i, v in out.worker_outputs():
+        seen.setdefault(i, []).append(v)
+    assert all(sorted(v) == [0.0, 1.0, 2.0] for v in seen.values())
+    assert out.server_stats["pulls"] == 48 and out.server_stats["pushes"] == 48
+    assert out.client_counters["issued"] == 48 and out.client_counters["credits"] == 8
+    table.close()
