@@ -17,7 +17,7 @@ for path in sorted(glob.glob("gpurun_out/b1[3-9]_*.json") + glob.glob("gpurun_ou
                  d["ms_per_step"], d["e2e"]["value"] / 1e9, ",".join(d["clocks"]["reasons"]) or "-",
                  os.path.basename(path)))
 rows.sort(key=lambda r: (r[1] != "fps_b200", r[0], not r[2], r[3] or 0))
-base = next((r[4] for r in rows if r[0] == 1 and r[1] == "fps_b200"), None)
+base = next((r[4] for r in rows if r[0] == 1 and r[1] == "fps_b200" and not r[2]), None)
 out = ["| N | impl | item cache | sync every | G updates/s (device) | ms/step | G updates/s (e2e) | weak-scaling eff. vs N=1 | clocks | file |",
        "|---|---|---|---|---|---|---|---|---|---|"]
 for r in rows:
