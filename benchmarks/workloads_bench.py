@@ -53,11 +53,12 @@ def main():
     c = torch.randint(0, a.vocab, (a.pairs,), generator=g, dtype=torch.int32).to(dev)
     o = torch.randint(0, a.vocab, (a.pairs,), generator=g, dtype=torch.int32).to(dev)
     ms = timed(lambda: m.step(c, o), a.steps)
+    m.flush(); torch.cuda.synchronize()
     m.check_finite()
     upd = a.pairs * 6 * world
     # per update: 2 rows of 1200 B pulled + 2 rows pushed
     res = {"w2v": {"dim": 300, "vocab": a.vocab, "negative": 5, "n_gpus": world, "ms_per_step": ms,
-                   "updates_per_s": upd / ms * 1e3, "row_GBs_per_gpu": a.pairs * 6 * 4 * 1200 / ms / 1e6}}
+                   "updates_per_s": upd / ms * 1e3, "replica_cache": m.rep_in is not None, "row_GBs_per_gpu": a.pairs * 6 * 4 * 1200 / ms / 1e6}}
     m.close()
     ctr = DeviceWideAndDeep(a.slots, 26, emb_dim=8, hidden=256, learning_rate=0.05, pull_limit=64, seed=1)
     ids = torch.randint(0, a.slots, (a.ctr_batch, 26), generator=g).to(dev)

@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from ...ops import native
 from ...runtime.device_stream import DevicePrefetcher
+from ...store.replica_cache import ReplicaCache
 from ...store.sharded_table import ShardedTable
 
 ERR_SIGMOID = 0  # reference parity: e = sigmoid(r - u.v)   (SGDUpdater.scala:8)
@@ -78,60 +79,34 @@ class DeviceOnlineMF:
             item_cache = self.world > 1 and os.environ.get("FPS_ITEM_CACHE", "1") != "0"
         self.item_cache = bool(item_cache)
         self.sync_every = max(1, int(sync_every))
-        if self.item_cache:
-            with torch.cuda.device(self.device):
-                n_pad = self.items.rows_per_shard * self.world
-                self.cache = torch.empty((n_pad, self.items.stride), dtype=torch.float32, device=self.cuda_device)
-                self.items.barrier()
-                all_ids = torch.arange(n_pad, device=self.cuda_device, dtype=torch.int64)
-                native.pull_gather(self.items.table_c, all_ids, self.cache)
-                self.base = self.cache.clone()
-                self.cache_c = native.local_table(self.cache, self.k)
-                self._since_sync = 0
-                self.sync_stream = torch.cuda.Stream(device=self.cuda_device)
-                self._syncs = []          # completion events of the background delta exchanges
+        self.replica = ReplicaCache(self.items, self.sync_every) if self.item_cache else None
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
-    def _launch_sync(self) -> None:
-        """Exchange deltas on the background stream (overlaps the next training kernels)."""
-        cur = torch.cuda.current_stream(self.cuda_device)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self.sync_stream.wait_event(ev)                    # include everything trained so far
-        with torch.cuda.stream(self.sync_stream):
-            native.cache_sync(self.items.table_c, self.cache, self.base)
-            done = torch.cuda.Event()
-            done.record(self.sync_stream)
-        self._syncs.append(done)
-        if len(self._syncs) > 2:                           # at most two exchanges outstanding
-            cur.wait_event(self._syncs.pop(0))
-        self._since_sync = 0
+    @property
+    def cache(self):
+        return self.replica.cache
+
+    @property
+    def base(self):
+        return self.replica.base
 
     def flush(self) -> None:
         """Item-cache mode: push every pending local delta to the master shards and wait for it."""
-        if not self.item_cache:
-            return
-        if self._since_sync > 0:
-            self._launch_sync()
-        cur = torch.cuda.current_stream(self.cuda_device)
-        for ev in self._syncs:
-            cur.wait_event(ev)
-        self._syncs = []
+        if self.replica is not None:
+            self.replica.flush()
 
     def step(self, users: torch.Tensor, items: Optional[torch.Tensor] = None,
              ratings: Optional[torch.Tensor] = None) -> None:
         """Process one micro-batch of ratings whose users belong to this worker (async SGD).
         ``step(packed)`` with a single int64 tensor takes packed64 records (``native.pack_ratings``)."""
         if self.item_cache:
-            native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.cache_c,
+            native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.replica.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=self.neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel="reg")
-            self._since_sync += 1
-            if self._since_sync >= self.sync_every:
-                self._launch_sync()
+            self.replica.after_step()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=self.neg,

@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from ..ops import native
+from ..store.replica_cache import ReplicaCache
 from ..store.sharded_table import ShardedTable
 
 ERR_LOGISTIC = 2
@@ -24,7 +25,8 @@ ERR_LOGISTIC = 2
 
 class DeviceSkipGram:
     def __init__(self, vocab: int, dim: int = 300, learning_rate: float = 0.025, negative: int = 5,
-                 group=None, seed: int = 0, device: Optional[int] = None):
+                 group=None, seed: int = 0, device: Optional[int] = None,
+                 replica_cache: Optional[bool] = None, sync_every: int = 4):
         self.vocab, self.dim, self.lr, self.negative, self.seed = vocab, dim, learning_rate, negative, seed
         b = 0.5 / dim
         self.w_in = ShardedTable(vocab, dim, group=group, device=device, init_range=(-b, b), seed=2 * seed + 1)
@@ -33,21 +35,39 @@ class DeviceSkipGram:
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.step_no = 0
+        # multi-GPU: train local replicas of both tables and exchange deltas in the background
+        # (store/replica_cache.py) instead of moving 2 x 1200 B per update over NVLink
+        if replica_cache is None:
+            replica_cache = self.w_in.world > 1
+        self.rep_in = ReplicaCache(self.w_in, sync_every) if replica_cache else None
+        self.rep_out = ReplicaCache(self.w_out, sync_every) if replica_cache else None
+        self._ones = None
 
     def step(self, centers: torch.Tensor, contexts: torch.Tensor) -> None:
-        ones = torch.ones(centers.numel(), dtype=torch.float32, device=self.dev)
-        native.mf_sgd_fused(centers, contexts, ones, self.w_in.table_c, 1, self.w_out.table_c, self.lr,
+        if self._ones is None or self._ones.numel() != centers.numel():
+            self._ones = torch.ones(centers.numel(), dtype=torch.float32, device=self.dev)
+        tin = self.rep_in.table_c if self.rep_in else self.w_in.table_c
+        tout = self.rep_out.table_c if self.rep_out else self.w_out.table_c
+        native.mf_sgd_fused(centers, contexts, self._ones, tin, 1, tout, self.lr,
                             err_mode=ERR_LOGISTIC, neg_rate=self.negative, num_items=self.vocab,
                             seed=self.seed, step=self.step_no, stats=self.stats, nan_flag=self.nan_flag,
                             kernel="reg")
+        if self.rep_in:
+            self.rep_in.after_step(); self.rep_out.after_step()
         self.step_no += 1
 
+    def flush(self) -> None:
+        if self.rep_in:
+            self.rep_in.flush(); self.rep_out.flush()
+
     def similarity(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        self.flush()
         va, vb = self.w_in.pull(a), self.w_in.pull(b)
         return torch.nn.functional.cosine_similarity(va, vb)
 
     def score(self, centers: torch.Tensor, contexts: torch.Tensor) -> torch.Tensor:
         """sigmoid(W_in[center] . W_out[context]) -- the model's co-occurrence probability."""
+        self.flush()
         u = self.w_in.pull(centers)
         return torch.sigmoid(self.w_out.pull_dot(contexts, torch.nn.functional.pad(
             u, (0, self.w_out.stride - u.shape[1])).contiguous()))
@@ -57,6 +77,7 @@ class DeviceSkipGram:
             raise FloatingPointError("non-finite skip-gram update")
 
     def barrier(self):
+        self.flush()
         self.w_in.barrier()
 
     def close(self):

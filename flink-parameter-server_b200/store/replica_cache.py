@@ -1,0 +1,74 @@
+"""Worker-side replica of a sharded table with background delta exchange (sender-side combining).
+
+``ReplicaCache(table)`` pulls a full local copy of ``table`` (row index == id).  Fused kernels train
+against ``replica.table_c`` (a single-shard ``ShardTable`` over local HBM); every ``sync_every`` calls
+of :meth:`after_step` a background stream runs ``fps_cache_sync``:
+
+  phase A: push ``replica - base`` to the master shards (one REDG per changed 16-byte chunk),
+           ``base <- value read``;
+  phase B: ``replica += master - base`` (the other workers' contributions, local REDG),
+           ``base <- master``.
+
+The invariant ``replica - base == local updates not yet pushed`` makes the exchange safe against
+concurrently running training kernels; nothing is lost, nothing needs a barrier, and a row crosses
+NVLink once per exchange instead of once per update.  This is the aggregated form of the reference's
+count / timer batching senders (M/common/CombinationLogic.scala) -- see DESIGN.md §2.1.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from ..ops import native
+from .sharded_table import ShardedTable
+
+
+class ReplicaCache:
+    def __init__(self, table: ShardedTable, sync_every: int = 4):
+        self.table = table
+        self.sync_every = max(1, int(sync_every))
+        dev = table.cuda_device
+        with torch.cuda.device(table.device):
+            n_pad = table.rows_per_shard * table.world
+            self.cache = torch.empty((n_pad, table.stride), dtype=torch.float32, device=dev)
+            table.barrier()
+            native.pull_gather(table.table_c, torch.arange(n_pad, device=dev, dtype=torch.int64), self.cache)
+            self.base = self.cache.clone()
+            self.table_c = native.local_table(self.cache, table.dim)
+            self.stream = torch.cuda.Stream(device=dev)
+        self._pending: List[torch.cuda.Event] = []
+        self._since_sync = 0
+        self.exchanges = 0
+        table.barrier()
+
+    def after_step(self) -> None:
+        self._since_sync += 1
+        if self._since_sync >= self.sync_every:
+            self.exchange()
+
+    def exchange(self) -> None:
+        """Start one delta exchange on the background stream (overlaps later training kernels)."""
+        dev = self.table.cuda_device
+        cur = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.stream.wait_event(ev)                    # include everything trained so far
+        with torch.cuda.stream(self.stream):
+            native.cache_sync(self.table.table_c, self.cache, self.base)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._pending.append(done)
+        if len(self._pending) > 2:                    # at most two exchanges outstanding
+            cur.wait_event(self._pending.pop(0))
+        self._since_sync = 0
+        self.exchanges += 1
+
+    def flush(self) -> None:
+        """Push every pending local delta to the masters and make the current stream wait for it."""
+        if self._since_sync > 0:
+            self.exchange()
+        cur = torch.cuda.current_stream(self.table.cuda_device)
+        for ev in self._pending:
+            cur.wait_event(ev)
+        self._pending = []

@@ -60,6 +60,25 @@ def main():
     if m.item_cache:
         assert torch.equal(m.cache[:ni, :k], V0), "replica != master after init"
         assert torch.equal(m.base, m.cache), "base != replica after init"
+    # word2vec with replica caches on both tables: one step, master must receive every delta
+    from fps_b200.models.w2v import DeviceSkipGram
+    sg = DeviceSkipGram(512 * world, 300, learning_rate=0.05, negative=0, seed=2)
+    sg.w_out.local.uniform_(-0.05, 0.05); sg.barrier()
+    if sg.rep_out is not None:                           # replicas were pulled before the uniform_ above
+        sg.rep_out.cache.copy_(sg.w_out.pull(torch.arange(sg.rep_out.cache.shape[0], device=dev), sg.rep_out.cache.clone()))
+        sg.rep_out.base.copy_(sg.rep_out.cache)
+    Win0 = sg.w_in.pull(torch.arange(512 * world, device=dev)); Wout0 = sg.w_out.pull(torch.arange(512 * world, device=dev))
+    gp = torch.Generator().manual_seed(9)
+    perm = torch.randperm(512 * world, generator=gp)
+    cen = perm[rank * 100:(rank + 1) * 100].to(dev); ctx = torch.randperm(512 * world, generator=gp)[rank * 100:(rank + 1) * 100].to(dev)
+    sg.step(cen.int(), ctx.int()); sg.barrier()
+    uu, vv = Win0[cen], Wout0[ctx]
+    gg = (0.05 * (1 - torch.sigmoid((uu * vv).sum(1))))[:, None]
+    dIn = torch.zeros_like(Win0).index_add_(0, cen, gg * vv); dOut = torch.zeros_like(Wout0).index_add_(0, ctx, gg * uu)
+    dist.all_reduce(dIn); dist.all_reduce(dOut)
+    torch.testing.assert_close(sg.w_in.pull(torch.arange(512 * world, device=dev)), Win0 + dIn, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sg.w_out.pull(torch.arange(512 * world, device=dev)), Wout0 + dOut, rtol=1e-5, atol=1e-6)
+    sg.close()
     U0 = m.users[:, :k].clone()
     m.barrier()
     m.step(my_users.int(), my_items.int(), ratings)
