@@ -64,9 +64,9 @@ def main():
     from fps_b200.models.w2v import DeviceSkipGram
     sg = DeviceSkipGram(512 * world, 300, learning_rate=0.05, negative=0, seed=2)
     sg.w_out.local.uniform_(-0.05, 0.05); sg.barrier()
-    if sg.rep_out is not None:                           # replicas were pulled before the uniform_ above
-        sg.rep_out.cache.copy_(sg.w_out.pull(torch.arange(sg.rep_out.cache.shape[0], device=dev), sg.rep_out.cache.clone()))
-        sg.rep_out.base.copy_(sg.rep_out.cache)
+    if sg.rep_out is not None:                           # the replica was pulled before the uniform_ above
+        from fps_b200.store.replica_cache import ReplicaCache
+        sg.rep_out = ReplicaCache(sg.w_out, 4)
     Win0 = sg.w_in.pull(torch.arange(512 * world, device=dev)); Wout0 = sg.w_out.pull(torch.arange(512 * world, device=dev))
     gp = torch.Generator().manual_seed(9)
     perm = torch.randperm(512 * world, generator=gp)
