@@ -125,15 +125,18 @@ __device__ __forceinline__ void tk_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <typename IdT, int MODE>
-__global__ void __launch_bounds__(TK_THREADS, 1)
+// MB = number of 128-row query blocks per CTA.  With MB = 2 every item tile fetched by TMA feeds two
+// UMMA_M=128 accumulators (256 query rows), which halves the L2 -> SM item traffic per FLOP; the CTA
+// then has 8 epilogue warps (warps 4..11) and uses all 512 TMEM columns (2 blocks x 2 buffers x 128).
+template <typename IdT, int MODE, int MB>
+__global__ void __launch_bounds__(128 + 128 * MB, 1)
     fps_topk_mma_kernel(const __grid_constant__ CUtensorMap item_map,
                         const __grid_constant__ TopkArgs a) {
   extern __shared__ __align__(1024) unsigned char tk_smem_raw[];
   const int KB = (a.stride + TK_KB_FLOATS - 1) / TK_KB_FLOATS;  // 128-byte K blocks
   const uint32_t kb_bytes = TK_M * 128;                         // one K block of a 128-row tile
-  unsigned char* sA = tk_smem_raw;                              // [KB][128 rows][128 B]
-  unsigned char* sB = sA + (size_t)KB * kb_bytes;               // [STAGES][KB][128 rows][128 B]
+  unsigned char* sA = tk_smem_raw;                              // [MB][KB][128 rows][128 B]
+  unsigned char* sB = sA + (size_t)MB * KB * kb_bytes;          // [STAGES][KB][128 rows][128 B]
   const int NS = a.n_stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NS * KB * kb_bytes);
   uint64_t* full = bars;                  // [STAGES] TMA -> MMA
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
   int tile_end = tile_begin + a.tiles_per_split;
   if (tile_end > a.n_tiles) tile_end = a.n_tiles;
   const int my_tiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
-  const int row0 = qb * TK_M;
+  const int row0 = qb * TK_M * MB;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -159,14 +162,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       tk_mbar_init(&tfull[s], 1);
-      tk_mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+      tk_mbar_init(&tempty[s], 4 * MB);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: 2 accumulators x 128 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      tk_smem(tmem_slot)),
-                 "r"(256));
+                 "r"(256 * MB));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
 
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
     const IdT* qids = reinterpret_cast<const IdT*>(a.q_ids);
     const int nvec = a.stride >> 2;
     const int chunks_per_row = KB * 8;
-    for (int t = threadIdx.x; t < TK_M * chunks_per_row; t += TK_THREADS) {
+    for (int t = threadIdx.x; t < MB * TK_M * chunks_per_row; t += blockDim.x) {
       const int r = t / chunks_per_row;
       const int cc = t - r * chunks_per_row;  // 16-byte chunk index along K
       const int kb = cc >> 3, c = cc & 7;
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
                                              : a.q_local + (size_t)row * a.stride;
         v = fps_ld_row4(src + 4 * cc);  // the PULL (local HBM or NVLink peer)
       }
-      unsigned char* dst = sA + (size_t)kb * kb_bytes + (size_t)r * 128 + ((c ^ (r & 7)) << 4);
+      const int mb = r >> 7, rr = r & 127;
+      unsigned char* dst = sA + ((size_t)mb * KB + kb) * kb_bytes + (size_t)rr * 128 + ((c ^ (rr & 7)) << 4);
       *reinterpret_cast<float4*>(dst) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
@@ -224,14 +228,17 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
         tk_mbar_wait(&tempty[acc], aph ^ 1u);  // epilogue drained this accumulator
         tk_mbar_wait(&full[s], ph);            // TMA landed the item tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TK_N;
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t a_addr = tk_smem(sA + (size_t)kb * kb_bytes);
-          const uint32_t b_addr = tk_smem(sB + ((size_t)s * KB + kb) * kb_bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte atom
-            tk_mma_tf32(d_tmem, tk_desc(a_addr + k * 32), tk_desc(b_addr + k * 32), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+        for (int mb = 0; mb < MB; ++mb) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MB + mb) * TK_N;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t a_addr = tk_smem(sA + ((size_t)mb * KB + kb) * kb_bytes);
+            const uint32_t b_addr = tk_smem(sB + ((size_t)s * KB + kb) * kb_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte atom
+              tk_mma_tf32(d_tmem, tk_desc(a_addr + k * 32), tk_desc(b_addr + k * 32), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            }
           }
         }
         tk_commit(&empty[s]);     // smem stage reusable once these MMAs retire
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const int ew = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int r = ew * 32 + lane;               // row inside the 128-row query block
+    const int emb = (warp - 4) >> 2;            // which 128-row query block this warp drains
+    const int r = emb * TK_M + ew * 32 + lane;  // row inside the CTA's query rows
     const int row = row0 + r;
     const bool row_ok = row < a.n_queries;
     const float th = (MODE == 2 && row_ok) ? a.theta[row] : 0.f;
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
       for (int c0 = 0; c0 < TK_N; c0 += 32) {
         uint32_t v[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must be converged here
-        tk_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TK_N + c0), v);
+        tk_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * MB + emb) * TK_N + c0), v);
         if (row_ok) {
         if (MODE == 1) {
           if (full_tile) {
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256 * MB));
   }
 }
 
@@ -344,31 +352,37 @@ extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, in
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return -1005;
   a.n_tiles = (a.n_items + TK_N - 1) / TK_N;
-  const int qblocks = (a.n_queries + TK_M - 1) / TK_M;
+  const int MBv = (a.n_queries > TK_M && KB <= 2) ? 2 : 1;   // 2 query blocks per CTA when smem allows
+  const int qblocks = (a.n_queries + TK_M * MBv - 1) / (TK_M * MBv);
   int splits = num_sms / qblocks;  // one wave of CTAs (1 CTA/SM: smem bound), no tail wave
   if (splits > a.n_tiles) splits = a.n_tiles;
   if (splits < 1) splits = 1;
   a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
   a.n_splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   const size_t blk = (size_t)KB * TK_M * 128;
-  int stages = (int)((220 * 1024 - blk - 2048) / blk);
+  int stages = (int)((220 * 1024 - blk * MBv - 2048) / blk);
   if (stages > TK_MAX_STAGES) stages = TK_MAX_STAGES;
   if (stages < 2) return -1003;
   a.n_stages = stages;
-  const size_t smem = blk * (1 + stages) + 16 * 8 + 16 + 1024;
+  const size_t smem = blk * (MBv + stages) + 16 * 8 + 16 + 1024;
   const int grid = qblocks * a.n_splits;
-#define TK_LAUNCH(IDT, MODE)                                                                       \
+#define TK_LAUNCH2(IDT, MODE, MBT)                                                                 \
   do {                                                                                             \
-    cudaError_t e = cudaFuncSetAttribute(fps_topk_mma_kernel<IDT, MODE>,                           \
+    cudaError_t e = cudaFuncSetAttribute(fps_topk_mma_kernel<IDT, MODE, MBT>,                      \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     if (e != cudaSuccess) return (int)e;                                                           \
-    fps_topk_mma_kernel<IDT, MODE><<<grid, TK_THREADS, smem, stream>>>(map, a);                    \
+    fps_topk_mma_kernel<IDT, MODE, MBT><<<grid, 128 + 128 * MBT, smem, stream>>>(map, a);          \
+  } while (0)
+#define TK_LAUNCH(IDT, MODE)                                                                       \
+  do {                                                                                             \
+    if (MBv == 2) TK_LAUNCH2(IDT, MODE, 2); else TK_LAUNCH2(IDT, MODE, 1);                         \
   } while (0)
   if (id_bytes == 8) {
     if (a.mode == 0) TK_LAUNCH(long long, 0); else if (a.mode == 1) TK_LAUNCH(long long, 1); else TK_LAUNCH(long long, 2);
   } else {
     if (a.mode == 0) TK_LAUNCH(int, 0); else if (a.mode == 1) TK_LAUNCH(int, 1); else TK_LAUNCH(int, 2);
   }
+#undef TK_LAUNCH2
 #undef TK_LAUNCH
   return (int)cudaGetLastError();
 }
