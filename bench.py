@@ -54,6 +54,9 @@ def parse():
     p.add_argument("--item-cache", default="auto", choices=["auto", "on", "off"],
                    help="worker-side item cache + per-step delta merge (default: on when N > 1)")
     p.add_argument("--sync-every", type=int, default=4, help="item-cache: merge every k micro-batches")
+    p.add_argument("--update-rule", default="parity", choices=["parity", "plain"],
+                   help="parity: the reference's e = sigmoid(r - u.v) (SGDUpdater.scala:8; always positive, so "
+                        "the squared error drifts up by design); plain: e = r - u.v (textbook SGD, loss falls)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: tma pipeline)")
     return p.parse_args()
@@ -139,7 +142,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from fps_b200.ops import native
-    from fps_b200.models.mf.device import DeviceOnlineMF, ERR_SIGMOID
+    from fps_b200.models.mf.device import DeviceOnlineMF, ERR_PLAIN, ERR_SIGMOID
 
     if a.impl == "nccl":
         from fps_b200.parallel.nccl_baseline import NcclOnlineMF as Model
@@ -147,7 +150,8 @@ def main():
         Model = DeviceOnlineMF
     cache = {"auto": None, "on": True, "off": False}[a.item_cache]
     model = Model(a.users, a.items, a.factors, learning_rate=a.lr, pull_limit=a.pull_limit,
-                  seed=1234, err_mode=ERR_SIGMOID, kernel=a.kernel, item_cache=cache,
+                  seed=1234, err_mode=ERR_SIGMOID if a.update_rule == "parity" else ERR_PLAIN,
+                  kernel=a.kernel, item_cache=cache,
                   sync_every=a.sync_every)
 
     # ---- synthetic ratings: users owned by this worker (user % W == rank), uniform items -------
@@ -248,7 +252,11 @@ def main():
                        "item_cache": bool(getattr(model, "item_cache", False)),
                        "sync_every": a.sync_every,
                        "record_format": a.format if a.impl == "fps_b200" else "arrays",
-                       "update_rule": "reference parity e=sigmoid(r-u.v), fp32 (reference: fp64 JVM)"},
+                       "update_rule": ("reference parity e=sigmoid(r-u.v) (SGDUpdater.scala:8): e>0 always, so the "
+                                       "reported mse drifts upward by design; --update-rule plain trains with "
+                                       "e=r-u.v at the same speed" if a.update_rule == "parity"
+                                       else "plain residual e=r-u.v"),
+                       "precision_note": "fp32 tables and math (reference: fp64 on the JVM)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms_max / a.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
