@@ -13,7 +13,6 @@ per direction per GPU (900 nominal).
 import json
 import os
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see fps_b200/__init__.py
 import sys
 
 import torch

@@ -6,7 +6,6 @@ import argparse
 import json
 import os
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see fps_b200/__init__.py
 import sys
 
 import torch

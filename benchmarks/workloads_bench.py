@@ -5,7 +5,6 @@
 """
 import os
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import argparse
 import json
 import sys

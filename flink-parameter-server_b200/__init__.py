@@ -12,12 +12,6 @@ Public surface (reference names kept):
 * device tier: :mod:`fps_b200.store` (sharded HBM tables), :mod:`fps_b200.ops` (sm_100a kernels),
   :mod:`fps_b200.parallel` (NVLink symmetric-heap fabric, partitioners, NCCL baseline)
 """
-import os as _os
-
-# Persistent kernels (device message tier) must not meet CUDA's lazy module loading: the first launch
-# of an unloaded kernel synchronises the context and would deadlock behind a resident server kernel.
-_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 from .api import (BatchedParameterServerClient, BatchedWorkerLogic, Either, Left,
                   LooseParameterServerLogic, LooseWorkerLogic, ParameterServer,
                   ParameterServerClient, ParameterServerLogic, Right, RuntimeContext, WorkerLogic)

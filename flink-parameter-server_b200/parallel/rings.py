@@ -6,7 +6,11 @@ per rank; ``DeviceMessageServer`` runs the persistent ``fps_server_loop`` kernel
 with the pull limiter implemented as a device-resident credit counter + FIFO spill queue.
 
 While a server kernel is resident never call ``torch.cuda.synchronize()`` (device-wide sync waits
-for the persistent kernel); synchronise streams / events instead.
+for the persistent kernel); synchronise streams / events instead.  Run such processes with
+``CUDA_MODULE_LOADING=EAGER`` (set before CUDA initialises): CUDA otherwise loads kernels lazily and the
+first launch of a not-yet-loaded kernel synchronises the context -- a deadlock behind a resident
+kernel.  ``start()`` pre-loads this library's kernels and the torch kernels the server / client use
+themselves, and warns when eager loading is not selected.
 """
 from __future__ import annotations
 
@@ -119,6 +123,12 @@ class DeviceMessageServer:
         self.running = False
 
     def start(self) -> None:
+        import os
+        import warnings
+
+        if os.environ.get("CUDA_MODULE_LOADING", "").upper() != "EAGER":
+            warnings.warn("persistent server kernel without CUDA_MODULE_LOADING=EAGER: any kernel first "
+                          "launched while the server is resident can deadlock (see parallel/rings.py)")
         # CUDA loads kernels lazily and the first launch of an unloaded kernel synchronises the
         # context -- a deadlock once the persistent kernel is resident.  Load everything used while
         # the server runs *now*: our ring kernels, and the torch kernels of stop()/stats()/clients.

@@ -1,9 +1,6 @@
 import os
 import sys
 
-# must be set before CUDA initialises: persistent server kernels deadlock against lazy module loading
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 import pytest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

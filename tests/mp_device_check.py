@@ -7,7 +7,7 @@ shards, and the fused MF step against a single-process fp32 PyTorch reference.
 """
 import os
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # see fps_b200/__init__.py
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # persistent server kernel below: see parallel/rings.py
 import sys
 
 import torch
