@@ -190,6 +190,35 @@ class DeviceOnlineMF:
         self.flush()
         return self.items.dump_local(only_touched=False)
 
+    # -- checkpoint / resume (the reference only has export + transformWithModelLoad) ------
+    def save(self, directory: str) -> str:
+        """Every rank writes its user partition and its item shard to ``directory/rank<r>.npz``."""
+        import numpy as np
+
+        os.makedirs(directory, exist_ok=True)
+        self.barrier()
+        uid, uvec = self.user_vectors()
+        iid, ivec = self.item_vectors()
+        path = os.path.join(directory, f"rank{self.rank}_of{self.world}.npz")
+        np.savez(path, user_ids=uid.cpu().numpy(), user_vecs=uvec.cpu().numpy(), item_ids=iid.cpu().numpy(),
+                 item_vecs=ivec.cpu().numpy(), step_no=self.step_no)
+        return path
+
+    def load(self, directory: str) -> None:
+        """Resume from :meth:`save` (same world size): users go back to their worker, items to their
+        shard (one-sided assign), replicas are re-pulled."""
+        import numpy as np
+
+        d = np.load(os.path.join(directory, f"rank{self.rank}_of{self.world}.npz"))
+        uid = torch.from_numpy(d["user_ids"]).to(self.cuda_device)
+        self.users[uid // self.world, : self.k] = torch.from_numpy(d["user_vecs"]).to(self.cuda_device)
+        self.items.load(torch.from_numpy(d["item_ids"]).to(self.cuda_device),
+                        torch.from_numpy(d["item_vecs"]).to(self.cuda_device))
+        self.step_no = int(d["step_no"])
+        self.items.barrier()
+        if self.replica is not None:
+            self.replica = ReplicaCache(self.items, self.sync_every)
+
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:
             raise FloatingPointError("non-finite SGD update (FactorIsNotANumberException)")

@@ -302,3 +302,19 @@ def test_item_cache_mode_single_gpu_matches_direct_mode(dev):
     torch.testing.assert_close(m_cache.cache[:ni], m_cache.items.local[:ni], rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(m_cache.base, m_cache.cache, rtol=1e-6, atol=1e-7)
     m_direct.close(); m_cache.close()
+
+
+def test_device_mf_checkpoint_resume(dev, tmp_path):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    g = torch.Generator().manual_seed(4)
+    u = torch.randint(0, 3000, (8192,), generator=g, dtype=torch.int32).cuda()
+    i = torch.randint(0, 2000, (8192,), generator=g, dtype=torch.int32).cuda()
+    r = torch.rand(8192, generator=g).cuda()
+    m = DeviceOnlineMF(3000, 2000, 32, learning_rate=0.05, seed=1)
+    m.step(u, i, r)
+    m.save(str(tmp_path))
+    m2 = DeviceOnlineMF(3000, 2000, 32, learning_rate=0.05, seed=99)      # different init, then resume
+    m2.load(str(tmp_path))
+    assert torch.equal(m2.users, m.users) and torch.equal(m2.items.local, m.items.local) and m2.step_no == 1
+    m.close(); m2.close()
