@@ -40,7 +40,8 @@ class DeviceOnlineMF:
                  group=None, seed: int = 0, err_mode: int = ERR_SIGMOID,
                  device: Optional[int] = None, track_touched: bool = False,
                  kernel: Optional[str] = None, item_cache: Optional[bool] = None,
-                 sync_every: int = 4):
+                 sync_every: int = 4, user_memory: int = 0,
+                 sync_interval_ms: Optional[float] = None):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -69,6 +70,13 @@ class DeviceOnlineMF:
                              seed * 2 + 2, range_min, range_max)
             self.stats = torch.zeros(2, dtype=torch.float32, device=self.cuda_device)
             self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.cuda_device)
+            # K5: per-user memory of recently seen items (userMemory of the reference, default 128
+            # there; 0 here = sample uniformly inside the fused kernel, rejecting only the positive)
+            self.user_memory = int(user_memory) if self.neg > 0 else 0
+            if self.user_memory > 0:
+                self.seen = torch.full((n_local, self.user_memory), -1, dtype=torch.int32,
+                                       device=self.cuda_device)
+                self.seen_pos = torch.zeros(n_local, dtype=torch.int32, device=self.cuda_device)
         # ---- item-cache mode (sender-side combining) --------------------------------------------
         # The worker trains a local replica of the item table (pulls and pushes stay in local HBM);
         # every `sync_every` micro-batches a background stream pushes (replica - base) to the master
@@ -79,7 +87,9 @@ class DeviceOnlineMF:
             item_cache = self.world > 1 and os.environ.get("FPS_ITEM_CACHE", "1") != "0"
         self.item_cache = bool(item_cache)
         self.sync_every = max(1, int(sync_every))
-        self.replica = ReplicaCache(self.items, self.sync_every) if self.item_cache else None
+        self.sync_interval_ms = sync_interval_ms
+        self.replica = (ReplicaCache(self.items, self.sync_every, sync_interval_ms)
+                        if self.item_cache else None)
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
@@ -100,16 +110,24 @@ class DeviceOnlineMF:
              ratings: Optional[torch.Tensor] = None) -> None:
         """Process one micro-batch of ratings whose users belong to this worker (async SGD).
         ``step(packed)`` with a single int64 tensor takes packed64 records (``native.pack_ratings``)."""
+        neg = self.neg
+        if self.user_memory > 0:
+            # negatives drawn by the sampler kernel against the per-user seen ring; the fused kernel
+            # then consumes the expanded batch as plain records
+            users, items, ratings = native.neg_sample(users, items, ratings, self.neg, self.num_items,
+                                                      self.seen, self.seen_pos, self.world,
+                                                      seed=self.seed, step=self.step_no)
+            neg = 0
         if self.item_cache:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.replica.table_c,
-                                self.lr, err_mode=self.err_mode, neg_rate=self.neg,
+                                self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel="reg")
             self.replica.after_step()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
-                                self.lr, err_mode=self.err_mode, neg_rate=self.neg,
+                                self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel=self.kernel)
@@ -217,7 +235,7 @@ class DeviceOnlineMF:
         self.step_no = int(d["step_no"])
         self.items.barrier()
         if self.replica is not None:
-            self.replica = ReplicaCache(self.items, self.sync_every)
+            self.replica = ReplicaCache(self.items, self.sync_every, self.sync_interval_ms)
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:

@@ -58,7 +58,8 @@ def _result(model: DeviceOnlineMF, seen_users: Optional[set]) -> ResultStream:
 def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learningRate=0.01,
                         negativeSampleRate=0, pullLimit=0, seed=0, plain_residual=False,
                         numUsers: Optional[int] = None, numItems: Optional[int] = None,
-                        batch_size: int = 1 << 16, group=None, epochs: int = 1) -> ResultStream:
+                        batch_size: int = 1 << 16, group=None, epochs: int = 1,
+                        userMemory: int = 128) -> ResultStream:
     recs = None
     if numUsers is None or numItems is None:
         recs = list(src.collect() if hasattr(src, "collect") else src)
@@ -70,7 +71,8 @@ def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learn
     model = DeviceOnlineMF(numUsers, numItems, numFactors, rangeMin, rangeMax, learningRate,
                            negativeSampleRate, pull_limit=pullLimit if pullLimit and pullLimit != 1600 else 0,
                            group=group, seed=seed, err_mode=ERR_PLAIN if plain_residual else ERR_SIGMOID,
-                           track_touched=True)
+                           track_touched=True,
+                           user_memory=min(int(userMemory), 256) if negativeSampleRate > 0 else 0)
     seen = set()
     data = list(_batches(src, batch_size))
     for b in data:

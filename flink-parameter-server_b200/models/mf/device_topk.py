@@ -25,13 +25,36 @@ from ...store.sharded_table import ShardedTable
 
 
 class DeviceTopK:
-    def __init__(self, items: torch.Tensor, max_batch_bytes: int = 512 << 20):
+    """``sort_by_length=True`` adds the LEMP LENGTH bound at tile granularity (K6;
+    LEMPPruningFunctions.scala:20-27, the bucket early-exit of PSTopKGeneratorWorker.scala:86-90): the
+    item table is kept sorted by vector length (descending), so every 128-item tile has a known
+    maximum length and a tile can contain a top-K item of query ``q`` only if
+    ``maxLen(tile) * |q| >= theta_q``.  The tiles that survive form a *prefix* of the table, so pruning
+    is simply running the same tensor-core kernel over fewer rows -- no pointer chasing."""
+
+    LENGTH_SLACK = 1.004  # TF32 products may exceed the fp32 Cauchy-Schwarz bound by ~2^-10 relative
+
+    def __init__(self, items: torch.Tensor, max_batch_bytes: int = 512 << 20, sort_by_length: bool = False):
         if items.dim() != 2 or items.shape[1] % 4 != 0:
             raise ValueError("items must be [n_items, stride] with stride % 4 == 0")
+        self.perm = None
+        if sort_by_length:
+            lens = items.norm(dim=1)
+            self.perm = torch.argsort(lens, descending=True)
+            items = items[self.perm].contiguous()
+            self.tile_maxlen = lens[self.perm][:: native.TOPK_TILE].contiguous()
         self.items = items
         self.n_items, self.stride = items.shape
         self.n_tiles = (self.n_items + native.TOPK_TILE - 1) // native.TOPK_TILE
         self.max_batch_bytes = max_batch_bytes
+        self.last_tiles_scored = (0, 0)   # (pass 1, pass 2) tiles actually scored by the last topk()
+
+    def _tiles_needed(self, theta: torch.Tensor, qnorm: torch.Tensor) -> int:
+        """Number of leading tiles that can still hold a score >= theta for at least one query."""
+        bound = torch.where((theta > 0) & (qnorm > 0), theta / qnorm.clamp_min(1e-30),
+                            torch.full_like(theta, -1.0))          # theta <= 0: the bound cannot prune
+        need = (self.tile_maxlen[None, :] * self.LENGTH_SLACK >= bound[:, None]).sum(1)
+        return int(need.max().item())
 
     # -- raw scores (validation / tiny problems) ---------------------------------------------
     def scores(self, *, q_ids=None, q_table: Optional[ShardedTable] = None, q_local=None) -> torch.Tensor:
@@ -60,17 +83,44 @@ class DeviceTopK:
             ql = q_local[a:b].contiguous() if q_local is not None else None
             tab = q_table.table_c if q_table is not None else None
             n = b - a
-            tile_max = torch.empty((n, self.n_tiles), dtype=torch.float32, device=dev)
-            native.topk_mma(self.items, 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
-            if self.n_tiles >= Kp:
+            T = native.TOPK_TILE
+            if self.perm is None:
+                p2 = self.n_tiles
+                tile_max = torch.empty((n, self.n_tiles), dtype=torch.float32, device=dev)
+                native.topk_mma(self.items, 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
+                p1 = self.n_tiles
+            else:
+                # LENGTH-pruned pass 1: score the tiles of the longest items first; their K-th best tile
+                # maximum already bounds how far down the length-sorted table a top-K item can sit.
+                q = q_table.pull(ids) if ids is not None else ql[:, : self.stride]
+                qnorm = q.norm(dim=1)
+                p1 = min(self.n_tiles, max(Kp, 8, self.n_tiles // 8))
+                tile_max = torch.empty((n, p1), dtype=torch.float32, device=dev)
+                native.topk_mma(self.items[: p1 * T], 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
+                if p1 >= Kp and p1 < self.n_tiles:
+                    theta0 = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
+                    p_ext = self._tiles_needed(theta0, qnorm)
+                else:
+                    p_ext = self.n_tiles
+                if p_ext > p1:
+                    more = torch.empty((n, p_ext - p1), dtype=torch.float32, device=dev)
+                    native.topk_mma(self.items[p1 * T: p_ext * T], 1, q_ids=ids, q_tab=tab, q_local=ql,
+                                    tile_max=more)
+                    tile_max = torch.cat([tile_max, more], 1)
+                    p1 = p_ext
+            if tile_max.shape[1] >= Kp:
                 theta = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
             else:
                 theta = torch.full((n,), -3.0e38, dtype=torch.float32, device=dev)
+            if self.perm is not None:
+                p2 = min(p1, self._tiles_needed(theta, qnorm)) if tile_max.shape[1] >= Kp else self.n_tiles
+            scored = self.items if p2 == self.n_tiles else self.items[: p2 * T]
+            self.last_tiles_scored = (p1, p2)
             for cap in (cap_small, cap_full):
                 cnt = torch.zeros(n, dtype=torch.int32, device=dev)
                 cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
                 ci = torch.empty((n, cap), dtype=torch.int32, device=dev)
-                native.topk_mma(self.items, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
+                native.topk_mma(scored, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
                                 cand_count=cnt, cand_score=cs, cand_item=ci)
                 if cap == cap_full or int(cnt.max().item()) <= cap:
                     break
@@ -85,6 +135,8 @@ class DeviceTopK:
                 exact = torch.einsum("qd,qkd->qk", q, self.items[rows])
                 order = torch.argsort(exact, dim=1, descending=True)
                 sc, rows = torch.gather(exact, 1, order), torch.gather(rows, 1, order)
+            if self.perm is not None:
+                rows = self.perm[rows]      # back to row numbers of the caller's (unsorted) table
             outs.append(sc); outi.append(rows)
         return torch.cat(outs), torch.cat(outi)
 

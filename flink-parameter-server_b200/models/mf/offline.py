@@ -96,7 +96,7 @@ def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: fl
         return ps_offline_mf_device(src, numFactors=numFactors, rangeMin=rangeMin, rangeMax=rangeMax,
                                     learningRate=learningRate, negativeSampleRate=negativeSampleRate,
                                     iterations=iterations, pullLimit=pullLimit, seed=seed or 0,
-                                    plain_residual=plain_residual, **device_kw)
+                                    userMemory=userMemory, plain_residual=plain_residual, **device_kw)
     initDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax,
                                                        None if seed is None else seed + 1)
     holder = {}

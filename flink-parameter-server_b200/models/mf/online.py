@@ -114,7 +114,7 @@ def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: flo
 
         return ps_online_mf_device(src, numFactors=numFactors, rangeMin=rangeMin, rangeMax=rangeMax,
                                    learningRate=learningRate, negativeSampleRate=negativeSampleRate,
-                                   pullLimit=pullLimit, seed=seed or 0,
+                                   pullLimit=pullLimit, seed=seed or 0, userMemory=userMemory,
                                    plain_residual=plain_residual, **device_kw)
     initDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax,
                                                        None if seed is None else seed + 1)

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256, MINB)
           user = users[pos];
           item = items[pos];
           rating = a.ratings[pos];
+          if (user < 0) ok[r] = false;  // record voided upstream (fps_neg_sample: no unseen item found)
         }
         if (j == 0) {
           rt[r] = rating;

@@ -285,6 +285,52 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     _bump()
 
 
+class NegArgsC(C.Structure):
+    """Mirror of ``struct NegArgs`` (csrc/fps_sampler.cu)."""
+
+    _fields_ = [
+        ("users", C.c_void_p), ("items", C.c_void_p), ("ratings", C.c_void_p),
+        ("n_pos", C.c_longlong), ("neg_rate", C.c_int), ("format", C.c_int),
+        ("num_items", C.c_longlong), ("seed", C.c_ulonglong), ("step", C.c_ulonglong),
+        ("seen", C.c_void_p), ("seen_pos", C.c_void_p), ("memory", C.c_int), ("user_div", C.c_int),
+        ("max_tries", C.c_int), ("pad_", C.c_int),
+        ("out_users", C.c_void_p), ("out_items", C.c_void_p), ("out_ratings", C.c_void_p),
+    ]
+
+
+def neg_sample(users: torch.Tensor, items: Optional[torch.Tensor], ratings: Optional[torch.Tensor],
+               neg_rate: int, num_items: int, seen: torch.Tensor, seen_pos: torch.Tensor, user_div: int,
+               seed: int = 0, step: int = 0, max_tries: int = 32):
+    """K5: expand a micro-batch with ``neg_rate`` rating-0 negatives per rating, none of which is in
+    the user's recent-items memory ``seen`` ([n_local_users, userMemory] int32 ring, updated in
+    place).  Returns ``(users, items, ratings)`` int32/int32/float32 of length ``n*(1+neg_rate)``;
+    a negative that could not be found in ``max_tries`` draws has user == -1 (skipped downstream).
+    ``items=None``: ``users`` holds packed64 records."""
+    _req(users, "users"); _req(seen, "seen", torch.int32); _req(seen_pos, "seen_pos", torch.int32)
+    packed = items is None
+    if not packed:
+        _req(items, "items"); _req(ratings, "ratings", torch.float32)
+    n = users.numel()
+    per = 1 + int(neg_rate)
+    dev = users.device
+    ou = torch.empty(n * per, dtype=torch.int32, device=dev)
+    oi = torch.empty(n * per, dtype=torch.int32, device=dev)
+    orat = torch.empty(n * per, dtype=torch.float32, device=dev)
+    a = NegArgsC()
+    a.users = users.data_ptr()
+    a.items = None if packed else items.data_ptr()
+    a.ratings = None if packed else ratings.data_ptr()
+    a.n_pos = n; a.neg_rate = int(neg_rate); a.format = 1 if packed else 0
+    a.num_items = int(max(num_items, 1)); a.seed = seed & (2**64 - 1); a.step = int(step)
+    a.seen = seen.data_ptr(); a.seen_pos = seen_pos.data_ptr(); a.memory = int(seen.shape[1])
+    a.user_div = int(user_div); a.max_tries = int(max_tries)
+    a.out_users = ou.data_ptr(); a.out_items = oi.data_ptr(); a.out_ratings = orat.data_ptr()
+    _check(lib().fps_neg_sample(C.byref(a), 4 if packed else _id_bytes(users),
+                                sm_count(dev.index), _stream()), "neg_sample")
+    _bump()
+    return ou, oi, orat
+
+
 PACK_USER_BITS, PACK_ITEM_BITS = 26, 22
 
 

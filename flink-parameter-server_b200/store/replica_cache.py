@@ -16,7 +16,8 @@ count / timer batching senders (M/common/CombinationLogic.scala) -- see DESIGN.m
 """
 from __future__ import annotations
 
-from typing import List
+import time
+from typing import List, Optional
 
 import torch
 
@@ -25,9 +26,18 @@ from .sharded_table import ShardedTable
 
 
 class ReplicaCache:
-    def __init__(self, table: ShardedTable, sync_every: int = 4):
+    def __init__(self, table: ShardedTable, sync_every: int = 4, sync_interval_ms: Optional[float] = None,
+                 require: str = "any"):
+        """Exchange trigger = the reference's combinable conditions (CountLogic / TimerLogic,
+        CombinationWorkerSender): ``sync_every`` micro-batches (count), ``sync_interval_ms`` since the
+        last exchange (timer), combined with ``require="any"`` (OR, default) or ``"all"`` (AND)."""
         self.table = table
         self.sync_every = max(1, int(sync_every))
+        self.sync_interval = None if sync_interval_ms is None else float(sync_interval_ms) / 1000.0
+        if require not in ("any", "all"):
+            raise ValueError("require must be 'any' or 'all'")
+        self.require = require
+        self._last_sync = time.monotonic()
         dev = table.cuda_device
         with torch.cuda.device(table.device):
             n_pad = table.rows_per_shard * table.world
@@ -44,7 +54,13 @@ class ReplicaCache:
 
     def after_step(self) -> None:
         self._since_sync += 1
-        if self._since_sync >= self.sync_every:
+        count_hit = self._since_sync >= self.sync_every
+        if self.sync_interval is None:
+            fire = count_hit
+        else:
+            timer_hit = time.monotonic() - self._last_sync >= self.sync_interval
+            fire = (count_hit or timer_hit) if self.require == "any" else (count_hit and timer_hit)
+        if fire:
             self.exchange()
 
     def exchange(self) -> None:
@@ -62,6 +78,7 @@ class ReplicaCache:
         if len(self._pending) > 2:                    # at most two exchanges outstanding
             cur.wait_event(self._pending.pop(0))
         self._since_sync = 0
+        self._last_sync = time.monotonic()
         self.exchanges += 1
 
     def flush(self) -> None:

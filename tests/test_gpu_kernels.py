@@ -318,3 +318,88 @@ def test_device_mf_checkpoint_resume(dev, tmp_path):
     m2.load(str(tmp_path))
     assert torch.equal(m2.users, m.users) and torch.equal(m2.items.local, m.items.local) and m2.step_no == 1
     m.close(); m2.close()
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_negative_sampler_respects_user_memory(dev, packed):
+    """K5 contract (PSOnlineMatrixFactorizationWorker.scala:61-78): negatives are never one of the
+    user's last `userMemory` items, the ring evicts the oldest item, positives pass through."""
+    from fps_b200.ops import native
+
+    n_users, n_items, mem, neg = 64, 48, 8, 3
+    seen = torch.full((n_users, mem), -1, dtype=torch.int32, device=dev)
+    pos = torch.zeros(n_users, dtype=torch.int32, device=dev)
+    g = torch.Generator().manual_seed(5)
+    history = {u: [] for u in range(n_users)}
+    for step in range(12):
+        users = torch.randperm(n_users, generator=g)[:40].to(torch.int32)       # distinct users per batch
+        items = torch.randint(0, n_items, (40,), generator=g, dtype=torch.int32)
+        ratings = torch.ones(40)
+        for u, i in zip(users.tolist(), items.tolist()):
+            history[u].append(i)
+        if packed:
+            rec = native.pack_ratings(users.cuda(), items.cuda(), ratings.cuda())
+            ou, oi, orat = native.neg_sample(rec, None, None, neg, n_items, seen, pos, 1, seed=3, step=step)
+        else:
+            ou, oi, orat = native.neg_sample(users.cuda(), items.cuda(), ratings.cuda(), neg, n_items, seen,
+                                             pos, 1, seed=3, step=step)
+        ou, oi, orat = ou.cpu().view(40, 1 + neg), oi.cpu().view(40, 1 + neg), orat.cpu().view(40, 1 + neg)
+        assert torch.equal(ou[:, 0], users) and torch.equal(oi[:, 0], items) and (orat[:, 0] == 1).all()
+        assert (orat[:, 1:] == 0).all()
+        for row, u in enumerate(users.tolist()):
+            recent = set(history[u][-mem:])
+            for j in range(1, 1 + neg):
+                if ou[row, j] >= 0:
+                    assert ou[row, j] == u and int(oi[row, j]) not in recent
+        assert (ou[:, 1:] >= 0).float().mean() > 0.95     # 8 of 48 items excluded: a draw almost always succeeds
+    for u in range(n_users):                              # ring content == last `mem` items of the user
+        assert sorted(x for x in seen[u].cpu().tolist() if x >= 0) == sorted(history[u][-mem:])
+    # a user who has seen everything gets voided negatives, which the fused kernel skips
+    seen2 = torch.arange(16, dtype=torch.int32, device=dev).repeat(4, 1).contiguous()
+    pos2 = torch.full((4,), 16, dtype=torch.int32, device=dev)
+    ou, oi, orat = native.neg_sample(torch.arange(4, dtype=torch.int32, device=dev),
+                                     torch.zeros(4, dtype=torch.int32, device=dev), torch.ones(4, device=dev),
+                                     2, 16, seen2, pos2, 1)
+    assert (ou.view(4, 3)[:, 1:] == -1).all()
+
+
+def test_device_mf_with_user_memory_skips_voided_records(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    m = DeviceOnlineMF(200, 16, 16, learning_rate=0.05, negative_sample_rate=2, seed=2, user_memory=16)
+    users = torch.arange(200, dtype=torch.int32, device=dev)
+    for it in range(16):     # after 16 steps every user has all 16 items in memory: no negatives left
+        m.stats.zero_()
+        m.step(users, torch.full((200,), it, dtype=torch.int32, device=dev), torch.ones(200, device=dev))
+    torch.cuda.synchronize()
+    assert m.stats[1].item() == 200         # last step: positives only, voided negatives skipped
+    m.stats.zero_()
+    m2 = DeviceOnlineMF(200, 1000, 16, learning_rate=0.05, negative_sample_rate=2, seed=2, user_memory=16)
+    m2.step(users, torch.zeros(200, dtype=torch.int32, device=dev), torch.ones(200, device=dev))
+    torch.cuda.synchronize()
+    assert m2.stats[1].item() == 600
+    m.check_finite(); m.close(); m2.close()
+
+
+def test_replica_exchange_count_and_timer_triggers(dev):
+    """Count / timer / any / all exchange conditions (CountLogic, TimerLogic, CombinationLogic)."""
+    import time
+    from fps_b200.store.replica_cache import ReplicaCache
+    from fps_b200.store.sharded_table import ShardedTable
+
+    t = ShardedTable(500, 16, seed=1)
+    rc = ReplicaCache(t, sync_every=3)
+    for _ in range(7):
+        rc.after_step()
+    assert rc.exchanges == 2
+    rc = ReplicaCache(t, sync_every=1000, sync_interval_ms=20)
+    rc.after_step(); assert rc.exchanges == 0
+    time.sleep(0.03); rc.after_step(); assert rc.exchanges == 1
+    rc = ReplicaCache(t, sync_every=2, sync_interval_ms=20, require="all")
+    rc.after_step(); rc.after_step(); assert rc.exchanges == 0      # count reached, timer not yet
+    time.sleep(0.03); rc.after_step(); assert rc.exchanges == 1
+    rc.cache[7, :16] += 1.0                                          # a local update ...
+    rc.flush(); torch.cuda.synchronize()
+    ids = torch.tensor([7], device=dev)
+    torch.testing.assert_close(t.pull(ids)[0, :16], rc.cache[7, :16])  # ... reaches the master on flush
+    t.close()

@@ -66,3 +66,29 @@ def test_topk_small_item_table_and_k_larger_than_tiles(dev):
     assert torch.equal(sc, ref.values)
     ms, mi = merge_partial_topk(torch.cat([sc, sc - 1000], 1), torch.cat([rows, rows], 1), 50)
     assert torch.equal(ms, sc) and torch.equal(mi, rows)
+
+
+def test_length_sorted_pruning_is_exact_and_skips_short_tiles(dev):
+    """LEMP LENGTH bound at tile granularity: skewed item lengths => only a prefix of the length-sorted
+    table is scored, and the result equals the unpruned top-K (same TF32 scores, caller's row ids)."""
+    from fps_b200.models.mf.device_topk import DeviceTopK
+
+    k, ni, K = 64, 60000, 50
+    g = torch.Generator(device="cpu").manual_seed(3)
+    scale = torch.exp(torch.randn(ni, 1, generator=g) * 1.2)            # log-normal lengths (popularity skew)
+    items = (torch.randn(ni, k, generator=g) * scale).to(dev).contiguous()
+    q = torch.randn(700, k, generator=g).to(dev)
+    plain, pruned = DeviceTopK(items), DeviceTopK(items, sort_by_length=True)
+    sc0, rows0 = plain.topk(K, q_local=q)
+    sc1, rows1 = pruned.topk(K, q_local=q)
+    p1, p2 = pruned.last_tiles_scored
+    assert p2 < pruned.n_tiles // 2 and p1 < pruned.n_tiles, (p1, p2, pruned.n_tiles)
+    torch.testing.assert_close(sc1, sc0, rtol=0, atol=0)
+    same = (rows1 == rows0) | (sc0 == torch.roll(sc0, 1, 1)) | (sc0 == torch.roll(sc0, -1, 1))
+    assert same.all()
+    # uniform lengths: nothing can be pruned, results still identical
+    items2 = torch.nn.functional.normalize(torch.randn(5000, k, generator=g), dim=1).to(dev).contiguous()
+    a, b = DeviceTopK(items2), DeviceTopK(items2, sort_by_length=True)
+    s_a, r_a = a.topk(20, q_local=q[:130]); s_b, r_b = b.topk(20, q_local=q[:130])
+    torch.testing.assert_close(s_b, s_a, rtol=0, atol=0)
+    assert b.last_tiles_scored[1] == b.n_tiles
