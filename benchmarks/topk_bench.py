@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--queries", type=int, default=2048)
     ap.add_argument("--factors", type=int, default=64)
     ap.add_argument("--K", type=int, default=100)
+    ap.add_argument("--skew", type=float, default=0.0,
+                    help="> 0: log-normal item lengths with this sigma (popularity skew) instead of U[0.05, 2.05)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -42,7 +44,10 @@ def main():
     users = ShardedTable(a.users, a.factors, seed=1, init_range=(-1, 1))
     items = ShardedTable(a.items, a.factors, seed=2, init_range=(-1, 1))
     # LEMP-style: make item lengths heterogeneous so tile pruning has something to prune
-    items.local.mul_(torch.rand(items.local.shape[0], 1, device=dev) * 2 + 0.05)
+    if a.skew > 0:
+        items.local.mul_(torch.exp(torch.randn(items.local.shape[0], 1, device=dev) * a.skew))
+    else:
+        items.local.mul_(torch.rand(items.local.shape[0], 1, device=dev) * 2 + 0.05)
     tk = DeviceTopK(items.local)
     q = torch.randint(0, a.users, (a.queries,), device=dev)
     tile_max = torch.empty((a.queries, tk.n_tiles), dtype=torch.float32, device=dev)
@@ -54,10 +59,20 @@ def main():
         return torch.topk(u @ items.local[:, : a.factors].T, a.K, dim=1)
 
     ms_torch = t_ms(torch_ref, iters=5, warm=2)
+    tkp = DeviceTopK(items.local, sort_by_length=True)       # LEMP LENGTH bound at tile granularity
+    ms_pruned = t_ms(lambda: tkp.topk(a.K, q_ids=q, q_table=users), iters=5, warm=2)
+    p1, p2 = tkp.last_tiles_scored
+    for name, t in (("plain", tk), ("pruned", tkp)):       # per-stage breakdown (synchronising trace)
+        t.trace = []; t._t0 = None
+        t.topk(a.K, q_ids=q, q_table=users)
+        print(name, " ".join(f"{lbl}={ms:.3f}" for lbl, ms in t.trace), file=sys.stderr)
+        t.trace = None
     flops = 2.0 * a.queries * a.items * a.factors
     print(json.dumps({"queries": a.queries, "items": a.items, "factors": a.factors, "K": a.K,
                       "pass1_ms": ms_pass1, "pass1_tf32_TFLOPs": flops / ms_pass1 / 1e9,
                       "topk_total_ms": ms_total, "queries_per_s": a.queries / ms_total * 1e3,
+                      "length_pruned_total_ms": ms_pruned, "tiles": tkp.n_tiles, "tiles_pass1": p1,
+                      "tiles_pass2": p2, "skew": a.skew,
                       "torch_matmul_topk_ms": ms_torch, "speedup_vs_torch": ms_torch / ms_total}))
 
 

@@ -47,88 +47,136 @@ class DeviceTopK:
         self.n_items, self.stride = items.shape
         self.n_tiles = (self.n_items + native.TOPK_TILE - 1) // native.TOPK_TILE
         self.max_batch_bytes = max_batch_bytes
-        self.last_tiles_scored = (0, 0)   # (pass 1, pass 2) tiles actually scored by the last topk()
+        self._last = (0, None, None)
+        self.trace = None                 # set to [] to collect (stage, ms) pairs (synchronising!)
+        self._t0 = None
 
-    def _tiles_needed(self, theta: torch.Tensor, qnorm: torch.Tensor) -> int:
-        """Number of leading tiles that can still hold a score >= theta for at least one query."""
+    def _mark(self, label: str) -> None:
+        if self.trace is None:
+            return
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if self._t0 is not None:
+            self.trace.append((label, (now - self._t0) * 1e3))
+        self._t0 = now
+
+    def _tiles_needed(self, theta: torch.Tensor, qnorm: torch.Tensor) -> torch.Tensor:
+        """int32 device scalar: number of leading tiles (of the length-sorted table) that can still hold
+        a score >= theta for at least one query of the batch.  Stays on the device: the scoring kernel
+        reads it as its tile limit, so pruning costs no host round trip."""
         bound = torch.where((theta > 0) & (qnorm > 0), theta / qnorm.clamp_min(1e-30),
                             torch.full_like(theta, -1.0))          # theta <= 0: the bound cannot prune
-        need = (self.tile_maxlen[None, :] * self.LENGTH_SLACK >= bound[:, None]).sum(1)
-        return int(need.max().item())
+        # the batch needs the prefix of its least selective query; tile_maxlen is descending
+        return (self.tile_maxlen * self.LENGTH_SLACK >= bound.min()).sum().to(torch.int32).reshape(1)
+
+    @property
+    def last_tiles_scored(self) -> Tuple[int, int]:
+        """(pass 1, pass 2) tiles scored by the last ``topk`` chunk (synchronises)."""
+        p1, lim1, lim2 = self._last
+        t1 = p1 if lim1 is None else max(p1, min(self.n_tiles, int(lim1.item())))
+        t2 = self.n_tiles if lim2 is None else min(self.n_tiles, int(lim2.item()))
+        return t1, t2
 
     # -- raw scores (validation / tiny problems) ---------------------------------------------
     def scores(self, *, q_ids=None, q_table: Optional[ShardedTable] = None, q_local=None) -> torch.Tensor:
+        """[n_q, n_items] scores in the caller's item order."""
         n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
         out = torch.empty((n_q, self.n_items), dtype=torch.float32, device=self.items.device)
         native.topk_mma(self.items, 0, q_ids=q_ids, q_tab=q_table.table_c if q_table else None,
                         q_local=q_local, out_scores=out)
+        if self.perm is not None:
+            unsorted = torch.empty_like(out)
+            unsorted[:, self.perm] = out
+            out = unsorted
         return out
 
     def topk(self, K: int, *, q_ids=None, q_table: Optional[ShardedTable] = None, q_local=None,
              rescore: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """Returns ``(scores [n_q, K'], item_rows [n_q, K'])`` best first, ``K' = min(K, n_items)``;
-        item_rows index the local item table."""
+        item_rows index the caller's item table."""
         n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
         Kp = min(K, self.n_items)
-        # worst case K*128 candidates per query (K tiles reach theta); typically a few x K.  Start
-        # with a small buffer and redo pass 2 with the worst-case capacity only if a row overflowed.
-        cap_full = min(self.n_items, max(Kp * native.TOPK_TILE, native.TOPK_TILE))
-        cap_small = min(cap_full, max(1024, 8 * Kp))
-        chunk = max(128, (self.max_batch_bytes // (cap_full * 8)) // 128 * 128)
-        outs, outi = [], []
+        T = native.TOPK_TILE
         dev = self.items.device
+        # candidate buffer: a few x K per query is typical (worst case K*128 and more with ties); an
+        # overflowing row raises its theta and repeats pass 2 instead of growing the buffer
+        cap = min(max(2048, 16 * Kp), max(T, (self.n_items + T - 1) // T * T) * 2)
+        per_row = self.n_tiles * 4 + cap * 8
+        chunk = max(256, (self.max_batch_bytes // per_row) // 256 * 256)
+        tab = q_table.table_c if q_table is not None else None
+        outs, outi = [], []
         for a in range(0, n_q, chunk):
             b = min(n_q, a + chunk)
             ids = q_ids[a:b].contiguous() if q_ids is not None else None
             ql = q_local[a:b].contiguous() if q_local is not None else None
-            tab = q_table.table_c if q_table is not None else None
             n = b - a
-            T = native.TOPK_TILE
-            if self.perm is None:
-                p2 = self.n_tiles
+            self._mark("start")
+            kw = dict(q_ids=ids, q_tab=tab, q_local=ql)
+            # ---- pass 1: per-(query, tile) maxima ------------------------------------------------
+            lim1 = lim2 = None
+            p1 = self.n_tiles
+            prune = self.perm is not None and self.n_tiles >= 16 and max(Kp, self.n_tiles // 8) < self.n_tiles
+            if not prune:
                 tile_max = torch.empty((n, self.n_tiles), dtype=torch.float32, device=dev)
-                native.topk_mma(self.items, 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
-                p1 = self.n_tiles
+                native.topk_mma(self.items, 1, tile_max=tile_max, **kw)
+                self._mark("pass1")
             else:
                 # LENGTH-pruned pass 1: score the tiles of the longest items first; their K-th best tile
                 # maximum already bounds how far down the length-sorted table a top-K item can sit.
-                q = q_table.pull(ids) if ids is not None else ql[:, : self.stride]
+                q = q_table.pull(ids) if ids is not None else ql
                 qnorm = q.norm(dim=1)
-                p1 = min(self.n_tiles, max(Kp, 8, self.n_tiles // 8))
-                tile_max = torch.empty((n, p1), dtype=torch.float32, device=dev)
-                native.topk_mma(self.items[: p1 * T], 1, q_ids=ids, q_tab=tab, q_local=ql, tile_max=tile_max)
-                if p1 >= Kp and p1 < self.n_tiles:
-                    theta0 = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
-                    p_ext = self._tiles_needed(theta0, qnorm)
-                else:
-                    p_ext = self.n_tiles
-                if p_ext > p1:
-                    more = torch.empty((n, p_ext - p1), dtype=torch.float32, device=dev)
-                    native.topk_mma(self.items[p1 * T: p_ext * T], 1, q_ids=ids, q_tab=tab, q_local=ql,
-                                    tile_max=more)
-                    tile_max = torch.cat([tile_max, more], 1)
-                    p1 = p_ext
-            if tile_max.shape[1] >= Kp:
-                theta = torch.topk(tile_max, Kp, dim=1).values[:, -1].contiguous()
-            else:
-                theta = torch.full((n,), -3.0e38, dtype=torch.float32, device=dev)
-            if self.perm is not None:
-                p2 = min(p1, self._tiles_needed(theta, qnorm)) if tile_max.shape[1] >= Kp else self.n_tiles
-            scored = self.items if p2 == self.n_tiles else self.items[: p2 * T]
-            self.last_tiles_scored = (p1, p2)
-            for cap in (cap_small, cap_full):
-                cnt = torch.zeros(n, dtype=torch.int32, device=dev)
-                cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
-                ci = torch.empty((n, cap), dtype=torch.int32, device=dev)
-                native.topk_mma(scored, 2, q_ids=ids, q_tab=tab, q_local=ql, theta=theta,
-                                cand_count=cnt, cand_score=cs, cand_item=ci)
-                if cap == cap_full or int(cnt.max().item()) <= cap:
+                p1 = max(Kp, self.n_tiles // 8)
+                tile_max = torch.full((n, self.n_tiles), -3.0e38, dtype=torch.float32, device=dev)
+                first = torch.full((1,), p1, dtype=torch.int32, device=dev)
+                native.topk_mma(self.items, 1, tile_max=tile_max, tile_limit=first, **kw)
+                self._mark("pass1a")
+                theta0 = native.row_kth_largest(tile_max, Kp, n_cols=p1)
+                lim1 = self._tiles_needed(theta0, qnorm)
+                native.topk_mma(self.items, 1, tile_max=tile_max, tile_lo=p1, tile_limit=lim1, **kw)
+                self._mark("pass1b")
+            theta = native.row_kth_largest(tile_max, Kp)     # -3e38 when there are fewer than K tiles
+            if prune:
+                lim2 = self._tiles_needed(theta, qnorm)       # <= tiles scored in pass 1 (theta >= theta0)
+            self._mark("theta")
+            # ---- pass 2: candidates >= theta, progressive tightening on overflow ---------------
+            _, n_splits, seg_cap = native.topk_geometry(self.items, n, 0, cap)
+            cnt = torch.empty((n, n_splits), dtype=torch.int32, device=dev)
+            cs = torch.empty((n, cap), dtype=torch.float32, device=dev)
+            ci = torch.zeros((n, cap), dtype=torch.int32, device=dev)
+            bad = None
+            for attempt in range(4):
+                cs.fill_(-3.0e38)                               # unused slots of a segment never win
+                native.topk_mma(self.items, 2, theta=theta, cand_count=cnt, cand_score=cs, cand_item=ci,
+                                tile_limit=lim2, **kw)
+                over = (cnt > seg_cap).any(dim=1)
+                self._mark("pass2")
+                if not bool(over.any().item()):                 # the one host sync of the pipeline
                     break
-            valid = torch.arange(cap, device=dev)[None, :] < cnt.clamp(max=cap)[:, None]
-            cs = torch.where(valid, cs, torch.full_like(cs, -3.0e38))
-            top = torch.topk(cs, Kp, dim=1)
-            rows = torch.gather(ci, 1, top.indices).to(torch.int64)
-            sc = top.values
+                if attempt == 3:
+                    bad = torch.nonzero(over).flatten()
+                    break
+                # K-th best of the candidates that were kept: a valid, higher lower bound
+                theta = torch.maximum(theta, native.row_kth_largest(cs, Kp))
+                if prune:
+                    lim2 = torch.minimum(lim2, self._tiles_needed(theta, qnorm))
+                self._mark("tighten")
+            self._last = (p1, lim1, lim2)
+            sc, rows = native.row_topk(cs, ci, Kp)               # select + sort, one CTA per row
+            self._mark("select")
+            rows = rows.to(torch.int64)
+            if bad is not None:
+                # rows that still overflow (e.g. thousands of items tied at theta, an all-zero query):
+                # brute force, always exact
+                bq = dict(q_ids=ids[bad].contiguous(), q_tab=tab) if ids is not None else \
+                    dict(q_local=ql[bad].contiguous())
+                for s0 in range(0, bad.numel(), 64):
+                    sel = bad[s0:s0 + 64]
+                    full = torch.empty((sel.numel(), self.n_items), dtype=torch.float32, device=dev)
+                    sub = {k: (v[s0:s0 + 64].contiguous() if torch.is_tensor(v) else v) for k, v in bq.items()}
+                    native.topk_mma(self.items, 0, out_scores=full, **sub)
+                    top = torch.topk(full, Kp, dim=1)
+                    sc[sel], rows[sel] = top.values, top.indices
             if rescore:
                 q = (q_table.pull(ids) if ids is not None else ql[:, : self.stride])
                 q = torch.nn.functional.pad(q, (0, self.stride - q.shape[1]))
@@ -147,7 +195,15 @@ def merge_partial_topk(scores: torch.Tensor, items: torch.Tensor, K: int,
     (CollectTopKFromEachWorker.scala:41-56)."""
     if seen_mask is not None:
         scores = torch.where(seen_mask, torch.full_like(scores, -3.0e38), scores)
-    top = torch.topk(scores, min(K, scores.shape[1]), dim=1)
+    Kp = min(K, scores.shape[1])
+    if scores.is_cuda and Kp <= 2048:
+        # device K-way merge (K12): select + sort in one kernel; it returns column positions so that
+        # item ids of any integer width can be gathered afterwards
+        n, C = scores.shape
+        pos = torch.arange(C, dtype=torch.int32, device=scores.device).expand(n, C).contiguous()
+        sc, where = native.row_topk(scores.contiguous().float(), pos, Kp)
+        return sc, torch.gather(items, 1, where.to(torch.int64))
+    top = torch.topk(scores, Kp, dim=1)
     return top.values, torch.gather(items, 1, top.indices)
 
 

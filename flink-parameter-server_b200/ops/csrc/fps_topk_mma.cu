@@ -46,10 +46,15 @@ struct TopkArgs {
   long long out_ld;
   float* tile_max;          // mode 1: [n_queries, n_tiles]
   const float* theta;       // mode 2: [n_queries]
-  int* cand_count;          // mode 2: [n_queries]
-  float* cand_score;        // mode 2: [n_queries, cand_cap]
+  int* cand_count;          // mode 2: [n_queries, n_splits] candidates found by each split (may exceed seg_cap)
+  float* cand_score;        // mode 2: [n_queries, cand_cap], split s owns columns [s*seg_cap, (s+1)*seg_cap)
   int* cand_item;           // mode 2: [n_queries, cand_cap]
   int cand_cap;
+  int seg_cap;              // cand_cap / n_splits (set by the launcher)
+  int tile_lo;              // first tile to score
+  int pad_;
+  const int* tile_limit;    // optional device scalar: score only tiles < min(n_tiles, *tile_limit)
+                            // (length-pruning bound computed on the device, no host round trip)
 };
 
 __device__ __forceinline__ uint32_t tk_smem(const void* p) {
@@ -149,10 +154,12 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
   const int lane = threadIdx.x & 31;
   const int qb = blockIdx.x / a.n_splits;
   const int split = blockIdx.x - qb * a.n_splits;
-  const int tile_begin = split * a.tiles_per_split;
-  int tile_end = tile_begin + a.tiles_per_split;
-  if (tile_end > a.n_tiles) tile_end = a.n_tiles;
-  const int my_tiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
+  // tiles are dealt round-robin to the splits (tile = tile_lo + split + i * n_splits): a device-side
+  // tile limit or a hot region of the table (length-sorted items) then stays balanced over the CTAs
+  int tiles_hi = a.n_tiles;
+  if (a.tile_limit != nullptr) tiles_hi = min(tiles_hi, *a.tile_limit);
+  const int first_tile = a.tile_lo + split;
+  const int my_tiles = first_tile < tiles_hi ? (tiles_hi - first_tile + a.n_splits - 1) / a.n_splits : 0;
   const int row0 = qb * TK_M * MB;
 
   if (threadIdx.x == 0) {
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
         const uint32_t ph = (uint32_t)((i / NS) & 1);
         tk_mbar_wait(&empty[s], ph ^ 1u);
         tk_mbar_expect_tx(&full[s], (uint32_t)KB * kb_bytes);
-        const int item0 = (tile_begin + i) * TK_N;
+        const int item0 = (first_tile + i * a.n_splits) * TK_N;
         for (int kb = 0; kb < KB; ++kb)
           tk_tma_load_2d(sB + ((size_t)s * KB + kb) * kb_bytes, &item_map, kb * TK_KB_FLOATS, item0,
                          &full[s]);
@@ -253,10 +260,17 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
     const int row = row0 + r;
     const bool row_ok = row < a.n_queries;
     const float th = (MODE == 2 && row_ok) ? a.theta[row] : 0.f;
+    int n_cand = 0;
+    float* seg_s = nullptr;
+    int* seg_i = nullptr;
+    if (MODE == 2 && row_ok) {
+      seg_s = a.cand_score + (size_t)row * a.cand_cap + (size_t)split * a.seg_cap;
+      seg_i = a.cand_item + (size_t)row * a.cand_cap + (size_t)split * a.seg_cap;
+    }
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const uint32_t aph = (uint32_t)((i >> 1) & 1);
-      const int tile = tile_begin + i;
+      const int tile = first_tile + i * a.n_splits;
       const int item0 = tile * TK_N;
       const bool full_tile = item0 + TK_N <= a.n_items;   // no per-element bound check needed
       tk_mbar_wait(&tfull[acc], aph);
@@ -278,7 +292,10 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
               if (item0 + c0 + j < a.n_items) tmax = fmaxf(tmax, __uint_as_float(v[j]));
           }
         } else if (MODE == 2) {
-          // candidates are rare: first a branch-free "any >= theta" test over the 32 columns
+          // candidates are rare: first a branch-free "any >= theta" test over the 32 columns.  The
+          // thread owns (row, split) for the whole kernel, so candidates go to a private segment of the
+          // row's buffer with a register cursor: no atomics, no memory round trip in the epilogue
+          // (a returning atomic per candidate / per chunk made pass 2 latency bound).
           float cmax = -3.0e38f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
@@ -287,12 +304,12 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
             for (int j = 0; j < 32; ++j) {
               const int item = item0 + c0 + j;
               const float sc = __uint_as_float(v[j]);
-              if (sc >= th && item < a.n_items) {
-                const int slot = atomicAdd(a.cand_count + row, 1);
-                if (slot < a.cand_cap) {
-                  a.cand_score[(size_t)row * a.cand_cap + slot] = sc;
-                  a.cand_item[(size_t)row * a.cand_cap + slot] = item;
+              if (sc >= th && (full_tile || item < a.n_items)) {
+                if (n_cand < a.seg_cap) {
+                  seg_s[n_cand] = sc;
+                  seg_i[n_cand] = item;
                 }
+                ++n_cand;
               }
             }
           }
@@ -309,6 +326,7 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
       __syncwarp();
       if (lane == 0) tk_mbar_arrive(&tempty[acc]);
     }
+    if (MODE == 2 && row_ok) a.cand_count[(size_t)row * a.n_splits + split] = n_cand;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -334,7 +352,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, int id_bytes,
+extern "C" int fps_topk_mma(TopkArgs* args_in, const float* item_table, int id_bytes,
                             int num_sms, cudaStream_t stream) {
   TopkArgs a = *args_in;
   if (a.n_queries <= 0 || a.n_items <= 0) return 0;
@@ -355,10 +373,18 @@ extern "C" int fps_topk_mma(const TopkArgs* args_in, const float* item_table, in
   const int MBv = (a.n_queries > TK_M && KB <= 2) ? 2 : 1;   // 2 query blocks per CTA when smem allows
   const int qblocks = (a.n_queries + TK_M * MBv - 1) / (TK_M * MBv);
   int splits = num_sms / qblocks;  // one wave of CTAs (1 CTA/SM: smem bound), no tail wave
-  if (splits > a.n_tiles) splits = a.n_tiles;
+  int span = a.n_tiles - a.tile_lo;  // tiles that may be scored (a device tile_limit can only lower it)
+  if (span < 1) span = 1;
+  if (splits > span) splits = span;
   if (splits < 1) splits = 1;
-  a.tiles_per_split = (a.n_tiles + splits - 1) / splits;
-  a.n_splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.tiles_per_split = (span + splits - 1) / splits;
+  a.n_splits = (span + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.seg_cap = a.cand_cap / a.n_splits;
+  args_in->n_splits = a.n_splits;   // the caller sizes cand_count [n_queries, n_splits] from these
+  args_in->seg_cap = a.seg_cap;
+  args_in->n_tiles = a.n_tiles;
+  if (a.mode < 0) return 0;         // geometry query only
+  if (a.mode == 2 && a.seg_cap < 1) return -1006;
   const size_t blk = (size_t)KB * TK_M * 128;
   int stages = (int)((220 * 1024 - blk * MBv - 2048) / blk);
   if (stages > TK_MAX_STAGES) stages = TK_MAX_STAGES;

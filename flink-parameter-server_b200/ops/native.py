@@ -421,6 +421,7 @@ class TopkArgsC(C.Structure):
         ("tiles_per_split", C.c_int),
         ("n_splits", C.c_int),
         ("mode", C.c_int),
+        ("n_stages", C.c_int),
         ("out_scores", C.c_void_p),
         ("out_ld", C.c_longlong),
         ("tile_max", C.c_void_p),
@@ -429,19 +430,37 @@ class TopkArgsC(C.Structure):
         ("cand_score", C.c_void_p),
         ("cand_item", C.c_void_p),
         ("cand_cap", C.c_int),
+        ("seg_cap", C.c_int),
+        ("tile_lo", C.c_int),
+        ("pad_", C.c_int),
+        ("tile_limit", C.c_void_p),
     ]
 
 
 TOPK_TILE = 128
 
 
+def topk_geometry(items: torch.Tensor, n_queries: int, tile_lo: int = 0, cand_cap: int = 0):
+    """``(n_tiles, n_splits, seg_cap)`` the scoring kernel will use for this problem: every query row
+    is handled by ``n_splits`` CTAs, each owning ``seg_cap = cand_cap // n_splits`` candidate slots."""
+    a = TopkArgsC()
+    a.n_queries = int(n_queries); a.n_items, a.stride = items.shape
+    a.mode = -1; a.tile_lo = int(tile_lo); a.cand_cap = int(cand_cap)
+    _check(lib().fps_topk_mma(C.byref(a), C.c_void_p(items.data_ptr()), 4,
+                              sm_count(items.device.index), _stream()), "topk_geometry")
+    return a.n_tiles, a.n_splits, a.seg_cap
+
+
 def topk_mma(items: torch.Tensor, mode: int, *, q_ids: Optional[torch.Tensor] = None,
              q_tab: Optional[ShardTableC] = None, q_local: Optional[torch.Tensor] = None,
              out_scores: Optional[torch.Tensor] = None, tile_max: Optional[torch.Tensor] = None,
              theta: Optional[torch.Tensor] = None, cand_count: Optional[torch.Tensor] = None,
-             cand_score: Optional[torch.Tensor] = None, cand_item: Optional[torch.Tensor] = None) -> None:
+             cand_score: Optional[torch.Tensor] = None, cand_item: Optional[torch.Tensor] = None,
+             tile_lo: int = 0, tile_limit: Optional[torch.Tensor] = None) -> None:
     """tcgen05 scoring kernel (K6): queries (pulled from ``q_tab`` by id, or ``q_local``) x local
-    ``items`` with a mode-dependent epilogue.  See csrc/fps_topk_mma.cu."""
+    ``items`` with a mode-dependent epilogue.  Only tiles ``tile_lo <= t < min(n_tiles, tile_limit[0])``
+    are scored (``tile_limit``: optional int32 device scalar).  Mode 2 fills per-split candidate
+    segments: ``cand_count`` is ``[n_q, n_splits]`` (see :func:`topk_geometry`).  csrc/fps_topk_mma.cu."""
     _req(items, "items", torch.float32)
     n_items, stride = items.shape
     a = TopkArgsC()
@@ -456,20 +475,69 @@ def topk_mma(items: torch.Tensor, mode: int, *, q_ids: Optional[torch.Tensor] = 
             raise ValueError("q_local stride must equal item table stride")
         a.q_ids = None; a.q_local = q_local.data_ptr(); n_q = q_local.shape[0]; idb = 4
     a.n_queries = n_q; a.n_items = n_items; a.stride = stride; a.mode = int(mode)
+    a.tile_lo = int(tile_lo)
+    if tile_limit is not None:
+        _req(tile_limit, "tile_limit", torch.int32)
+        a.tile_limit = tile_limit.data_ptr()
+    n_tiles = (n_items + TOPK_TILE - 1) // TOPK_TILE
     if mode == 0:
         _req(out_scores, "out_scores", torch.float32)
         a.out_scores = out_scores.data_ptr(); a.out_ld = out_scores.stride(0)
     elif mode == 1:
         _req(tile_max, "tile_max", torch.float32)
-        assert tile_max.shape == (n_q, (n_items + TOPK_TILE - 1) // TOPK_TILE)
+        if tuple(tile_max.shape) != (n_q, n_tiles):
+            raise ValueError(f"tile_max must be [{n_q}, {n_tiles}]")
         a.tile_max = tile_max.data_ptr()
     else:
+        _req(theta, "theta", torch.float32); _req(cand_count, "cand_count", torch.int32)
+        _req(cand_score, "cand_score", torch.float32); _req(cand_item, "cand_item", torch.int32)
         a.theta = theta.data_ptr(); a.cand_count = cand_count.data_ptr()
         a.cand_score = cand_score.data_ptr(); a.cand_item = cand_item.data_ptr()
         a.cand_cap = cand_score.shape[1]
+        _, n_splits, _ = topk_geometry(items, n_q, tile_lo, a.cand_cap)
+        if tuple(cand_count.shape) != (n_q, n_splits):
+            raise ValueError(f"cand_count must be [{n_q}, {n_splits}] (topk_geometry)")
     _check(lib().fps_topk_mma(C.byref(a), C.c_void_p(items.data_ptr()), idb,
                               sm_count(items.device.index), _stream()), "topk_mma")
     _bump()
+
+
+def row_kth_largest(x: torch.Tensor, K: int, counts: Optional[torch.Tensor] = None,
+                    n_cols: Optional[int] = None) -> torch.Tensor:
+    """K-th largest value of every row of ``x`` [n, L] (only the first ``n_cols`` columns if given);
+    rows with fewer than ``K`` valid entries (``counts[row] < K``) give -3e38.  Radix select,
+    csrc/fps_select.cu."""
+    _req(x, "x", torch.float32)
+    if counts is not None:
+        _req(counts, "counts", torch.int32)
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    cols = int(x.shape[1] if n_cols is None else min(n_cols, x.shape[1]))
+    _check(lib().fps_row_kth(C.c_void_p(x.data_ptr()), C.c_longlong(x.stride(0)), int(x.shape[0]),
+                             cols, C.c_void_p(counts.data_ptr() if counts is not None else None),
+                             int(K), C.c_void_p(out.data_ptr()), _stream()), "row_kth")
+    _bump()
+    return out
+
+
+def row_topk(scores: torch.Tensor, items: torch.Tensor, K: int, counts: Optional[torch.Tensor] = None):
+    """Sorted (descending) top-``K`` ``(score, item)`` of every row of the candidate arrays
+    ``scores`` / ``items`` [n, cap] (int32 items); ``counts[row]`` limits the valid prefix.  Missing
+    entries are ``(-3e38, -1)``; equal scores are ordered by ascending item."""
+    _req(scores, "scores", torch.float32); _req(items, "items", torch.int32)
+    if scores.shape != items.shape or scores.stride(0) != items.stride(0):
+        raise ValueError("scores and items must have the same shape and row stride")
+    if counts is not None:
+        _req(counts, "counts", torch.int32)
+    n = scores.shape[0]
+    out_s = torch.empty((n, K), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((n, K), dtype=torch.int32, device=scores.device)
+    _check(lib().fps_row_topk(C.c_void_p(scores.data_ptr()), C.c_void_p(items.data_ptr()),
+                              C.c_longlong(scores.stride(0)), int(n), int(scores.shape[1]),
+                              C.c_void_p(counts.data_ptr() if counts is not None else None), int(K),
+                              C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()), _stream()),
+           "row_topk")
+    _bump()
+    return out_s, out_i
 
 
 class PaArgsC(C.Structure):

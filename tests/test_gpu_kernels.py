@@ -399,7 +399,7 @@ def test_replica_exchange_count_and_timer_triggers(dev):
     rc.after_step(); rc.after_step(); assert rc.exchanges == 0      # count reached, timer not yet
     time.sleep(0.03); rc.after_step(); assert rc.exchanges == 1
     rc.cache[7, :16] += 1.0                                          # a local update ...
-    rc.flush(); torch.cuda.synchronize()
+    rc.exchange(); rc.flush(); torch.cuda.synchronize()
     ids = torch.tensor([7], device=dev)
     torch.testing.assert_close(t.pull(ids)[0, :16], rc.cache[7, :16])  # ... reaches the master on flush
     t.close()

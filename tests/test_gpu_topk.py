@@ -92,3 +92,50 @@ def test_length_sorted_pruning_is_exact_and_skips_short_tiles(dev):
     s_a, r_a = a.topk(20, q_local=q[:130]); s_b, r_b = b.topk(20, q_local=q[:130])
     torch.testing.assert_close(s_b, s_a, rtol=0, atol=0)
     assert b.last_tiles_scored[1] == b.n_tiles
+
+
+@pytest.mark.parametrize("n,L,K", [(37, 100, 1), (64, 7813, 100), (5, 50000, 257), (16, 1024, 1024), (9, 300, 50)])
+def test_row_kth_largest_matches_torch(dev, n, L, K):
+    from fps_b200.ops import native
+
+    g = torch.Generator(device="cpu").manual_seed(n * L)
+    x = (torch.randn(n, L, generator=g) * torch.exp(torch.randn(n, 1, generator=g) * 3)).to(dev)
+    x[0, : L // 2] = x[0, 0]                                   # many equal values in one row
+    if n > 2:
+        x[1] = -x[1].abs()                                     # all negative
+        x[2, ::3] = 0.0
+    ref = torch.topk(x, K, dim=1).values[:, -1]
+    assert torch.equal(native.row_kth_largest(x, K), ref)
+    counts = torch.randint(0, L + 1, (n,), generator=g, dtype=torch.int32).to(dev)
+    got = native.row_kth_largest(x, K, counts=counts)
+    for r in range(n):
+        c = int(counts[r])
+        want = torch.topk(x[r, :c], K).values[-1].item() if c >= K else -3.0e38
+        assert got[r].item() == pytest.approx(want, rel=0, abs=0) or (c < K and got[r].item() < -2.9e38)
+
+
+@pytest.mark.parametrize("n,cap,K", [(33, 1024, 100), (7, 8192, 1000), (20, 300, 50), (4, 60000, 10), (12, 64, 64)])
+def test_row_topk_sorted_matches_torch(dev, n, cap, K):
+    from fps_b200.ops import native
+
+    g = torch.Generator(device="cpu").manual_seed(cap + K)
+    cs = torch.randn(n, cap, generator=g).to(dev)
+    ci = torch.stack([torch.randperm(cap * 3, generator=g)[:cap] for _ in range(n)]).to(torch.int32).to(dev)
+    ref = torch.topk(cs, K, dim=1)
+    s, i = native.row_topk(cs, ci, K)
+    assert torch.equal(s, ref.values) and torch.equal(i, torch.gather(ci, 1, ref.indices))
+    counts = torch.randint(0, cap + 1, (n,), generator=g, dtype=torch.int32).to(dev)
+    counts[0] = 0
+    s, i = native.row_topk(cs, ci, K, counts=counts)
+    for r in range(n):
+        c = int(counts[r]); kk = min(K, c)
+        want = torch.topk(cs[r, :c], kk)
+        assert torch.equal(s[r, :kk], want.values) and torch.equal(i[r, :kk], ci[r, :c][want.indices])
+        assert (s[r, kk:] < -2.9e38).all() and (i[r, kk:] == -1).all()
+    # ties: equal scores come out by ascending item id
+    cs2 = torch.full((3, 500), -1.0, device=dev); cs2[:, :7] = 1.0; cs2[:, 7:37] = 0.0
+    ci2 = torch.arange(500, 0, -1, dtype=torch.int32, device=dev).repeat(3, 1).contiguous()
+    s, i = native.row_topk(cs2, ci2, 20)
+    assert (s[:, :7] == 1).all() and (s[:, 7:] == 0).all()
+    assert torch.equal(i[0, :7], torch.arange(494, 501, dtype=torch.int32, device=dev))
+    assert torch.equal(i[0, 7:], torch.arange(464, 477, dtype=torch.int32, device=dev))
