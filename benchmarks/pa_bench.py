@@ -16,7 +16,10 @@ def main():
 
     feats, n, nnz = 5_000_000, 16384, 256
     res = {}
-    for name, L, binary in [("binary_PA", 1, True), ("ova32_PAI", 32, False)]:
+    from fps_b200.ops import native
+    for name, L, binary in [("binary_PA", 1, True), ("binary_PA_block_kernel", 1, True), ("ova4_PAI", 4, False),
+                            ("ova32_PAI", 32, False)]:
+        native.lib().fps_set_pa_variant(1 if "block_kernel" in name else 0)
         pa = DevicePassiveAggressive(feats, L, binary, "PA" if binary else "PAI", 1.0)
         g = torch.Generator(device="cpu").manual_seed(0)
         cols = torch.randint(0, feats, (n * nnz,), generator=g, dtype=torch.int32).to(dev)

@@ -42,15 +42,27 @@ def test_binary_sequential_matches_host_algorithm(algo_name, C, range_part):
     pa.close()
 
 
+@pytest.mark.parametrize("L,block_kernel", [(5, False), (3, False), (37, False), (5, True)])
 @pytest.mark.parametrize("which", ["OVA_PA", "OVA_PAI", "PB", "ML"])
-def test_multiclass_sequential_matches_host_algorithm(which):
+def test_multiclass_sequential_matches_host_algorithm(which, L, block_kernel):
+    """warp-per-example kernel with 2 / 1 / 16 lanes per row, and the block-per-example kernel."""
+    from fps_b200.ops import native
+
+    native.lib().fps_set_pa_variant(1 if block_kernel else 0)
+    try:
+        _multiclass_case(which, L)
+    finally:
+        native.lib().fps_set_pa_variant(0)
+
+
+def _multiclass_case(which, L):
     from fps_b200.models.pa.algorithms import PassiveAggressiveCostBased as CB
     from fps_b200.models.pa.algorithms import PassiveAggressiveOneVersusAll as OVA
     from fps_b200.models.pa.device import DevicePassiveAggressive, algo_to_device
 
     torch.cuda.set_device(0)
     r = random.Random(2)
-    feats, L = 500, 5
+    feats = 500
     cost = lambda a, b: 0.0 if a == b else 1.0 + 0.25 * abs(a - b)
     host = {"OVA_PA": OVA.buildPA(L), "OVA_PAI": OVA.buildPAI(L, 0.1), "PB": CB.buildPB(cost, L),
             "ML": CB.buildML(cost, L)}[which]
