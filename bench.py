@@ -53,6 +53,8 @@ def parse():
     p.add_argument("--item-cache", default="auto", choices=["auto", "on", "off"],
                    help="worker-side item cache + per-step delta merge (default: on when N > 1)")
     p.add_argument("--sync-every", type=int, default=4, help="item-cache: merge every k micro-batches")
+    p.add_argument("--item-blocking", default="auto", choices=["auto", "on", "off"],
+                   help="deal every micro-batch into <=16 MB item-table buckets before the fused kernel (L2 blocking)")
     p.add_argument("--update-rule", default="parity", choices=["parity", "plain"],
                    help="parity: the reference's e = sigmoid(r - u.v) (SGDUpdater.scala:8; always positive, so "
                         "the squared error drifts up by design); plain: e = r - u.v (textbook SGD, loss falls)")
@@ -148,10 +150,11 @@ def main():
     else:
         Model = DeviceOnlineMF
     cache = {"auto": None, "on": True, "off": False}[a.item_cache]
+    extra = {} if a.impl == "nccl" else {"item_blocking": {"auto": None, "on": True, "off": False}[a.item_blocking]}
     model = Model(a.users, a.items, a.factors, learning_rate=a.lr, pull_limit=a.pull_limit,
                   seed=1234, err_mode=ERR_SIGMOID if a.update_rule == "parity" else ERR_PLAIN,
                   kernel=a.kernel, item_cache=cache,
-                  sync_every=a.sync_every)
+                  sync_every=a.sync_every, **extra)
 
     # ---- synthetic ratings: users owned by this worker (user % W == rank), uniform items -------
     g = torch.Generator().manual_seed(1000 + rank)
@@ -250,6 +253,9 @@ def main():
                        "pull_limit": a.pull_limit or "hardware max rows in flight",
                        "item_cache": bool(getattr(model, "item_cache", False)),
                        "sync_every": a.sync_every,
+                       "item_blocking": (f"{model.block_buckets} buckets of {1 << model.block_shift} item rows, "
+                                         "reordered inside the timed step (2 extra kernels)"
+                                         if getattr(model, "item_blocking", False) else False),
                        "record_format": a.format if a.impl == "fps_b200" else "arrays",
                        "update_rule": ("reference parity e=sigmoid(r-u.v) (SGDUpdater.scala:8): e>0 always, so the "
                                        "reported mse drifts upward by design; --update-rule plain trains with "

@@ -41,7 +41,8 @@ class DeviceOnlineMF:
                  device: Optional[int] = None, track_touched: bool = False,
                  kernel: Optional[str] = None, item_cache: Optional[bool] = None,
                  sync_every: int = 4, user_memory: int = 0,
-                 sync_interval_ms: Optional[float] = None):
+                 sync_interval_ms: Optional[float] = None, item_blocking: Optional[bool] = None,
+                 block_bytes: int = 16 << 20):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -90,6 +91,25 @@ class DeviceOnlineMF:
         self.sync_interval_ms = sync_interval_ms
         self.replica = (ReplicaCache(self.items, self.sync_every, sync_interval_ms)
                         if self.item_cache else None)
+        # ---- L2 blocking: deal each micro-batch into buckets of <= 16 MB of item rows (fps_bucket.cu) ----
+        # only where the item rows are read from local HBM (single GPU, or the local replica)
+        row_bytes = self.items.stride * 4
+        if item_blocking is None:
+            item_blocking = ((self.world == 1 or self.item_cache) and self.num_items * row_bytes > (48 << 20)
+                             and (self.neg == 0 or self.user_memory > 0)
+                             and os.environ.get("FPS_ITEM_BLOCKING", "1") != "0")
+        self.item_blocking = bool(item_blocking)
+        block_bytes = int(os.environ.get("FPS_BLOCK_BYTES", block_bytes))
+        self.l2_hints = self.item_blocking and os.environ.get("FPS_L2_HINTS", "0") == "1"
+        per_bucket = max(1, int(block_bytes) // row_bytes)
+        self.block_shift = max(0, per_bucket.bit_length() - 1)
+        while -(-self.num_items >> self.block_shift) > native.BUCKET_MAX:
+            self.block_shift += 1
+        self.block_buckets = max(1, -(-self.num_items >> self.block_shift))
+        if self.item_blocking:
+            with torch.cuda.device(self.device):
+                self._bucket_scratch = torch.zeros(2 * native.BUCKET_MAX, dtype=torch.int32,
+                                                   device=self.cuda_device)
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
@@ -118,19 +138,23 @@ class DeviceOnlineMF:
                                                       self.seen, self.seen_pos, self.world,
                                                       seed=self.seed, step=self.step_no)
             neg = 0
+        if self.item_blocking and self.block_buckets > 1:
+            users, items, ratings = native.bucket_by_item(users, items, ratings, self.block_shift,
+                                                          self.block_buckets, self._bucket_scratch)
         if self.item_cache:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.replica.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
-                                max_inflight_rows=self.pull_limit, kernel="reg")
+                                max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints)
             self.replica.after_step()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
-                                max_inflight_rows=self.pull_limit, kernel=self.kernel)
+                                max_inflight_rows=self.pull_limit, kernel=self.kernel,
+                                l2_hints=self.l2_hints)
         self.step_no += 1
 
     def make_graph_step(self, batch_size: int, packed: bool = True):

@@ -73,6 +73,14 @@ class DeviceSketch:
         t = torch.tensor(tweets, dtype=torch.int64).to(self.dev, non_blocking=True)
         native.sketch_update(self.table.table_c, self.kind, k, t, self.num_hashes, self.array_size)
 
+    def update_ids(self, keys: torch.Tensor, tweets: torch.Tensor) -> None:
+        """Tensor fast path: ``keys`` int32 dense key slots (already interned, < capacity) and
+        ``tweets`` int64 tweet ids of the (word, tweet) occurrences, on the device or in pinned host
+        memory.  One kernel, ``num_hashes`` one-sided reductions per occurrence."""
+        k = keys.to(self.dev, non_blocking=True)
+        t = tweets.to(self.dev, non_blocking=True)
+        native.sketch_update(self.table.table_c, self.kind, k, t, self.num_hashes, self.array_size)
+
     # -- export (the close() dump of the *PSLogic classes) -------------------------------------
     def model(self) -> List[Tuple[int, object]]:
         torch.cuda.synchronize()

@@ -110,6 +110,32 @@ __device__ __forceinline__ void fps_red_add4(float* p, float4 v) {
                : "memory");
 }
 
+// L2 eviction-priority variants (createpolicy + .L2::cache_hint): used by the L2-blocked MF step to
+// keep the current item bucket resident (evict_last) while the once-touched user rows stream through
+// (evict_first).
+__device__ __forceinline__ unsigned long long fps_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long fps_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 fps_ld_row4_hint(const float* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void fps_red_add4_hint(float* p, float4 v, unsigned long long pol) {
+  asm volatile("red.relaxed.sys.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
+
 // ---- Philox4x32-10 counter RNG (K4: init is a pure function of (seed, id, column)) -----
 struct Philox4 {
   uint32_t x, y, z, w;

@@ -91,11 +91,18 @@ struct MfArgs {
   int user_sharded;           //   (word2vec: input vectors and output vectors are both PS tables)
   int use_push_tab;           // != 0: item deltas are pushed into push_tab instead of item_tab
   ShardTable push_tab;        //   (worker-side delta staging of the item-cache mode, see fps_cache_sync)
+  int l2_hints;               // != 0: item rows evict_last, user rows evict_first (L2-blocked batches)
+  int pad2_;
 };
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
 __global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
+  unsigned long long pol_user = 0, pol_item = 0;
+  if (HINT) {
+    pol_user = fps_policy_evict_first();
+    pol_item = fps_policy_evict_last();
+  }
   const int lane = threadIdx.x & (LPR - 1);
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
   const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
@@ -161,8 +168,13 @@ __global__ void __launch_bounds__(256, MINB)
       for (int c = 0; c < VPL; ++c) {
         const int q = lane + c * LPR;
         if (ok[r] && q < nvec) {
-          v[r][c] = fps_ld_row4(vp[r] + 4 * q);  // the PULL
-          u[r][c] = *reinterpret_cast<const float4*>(up[r] + 4 * q);
+          if (HINT) {
+            v[r][c] = fps_ld_row4_hint(vp[r] + 4 * q, pol_item);  // the PULL
+            u[r][c] = fps_ld_row4_hint(up[r] + 4 * q, pol_user);
+          } else {
+            v[r][c] = fps_ld_row4(vp[r] + 4 * q);  // the PULL
+            u[r][c] = *reinterpret_cast<const float4*>(up[r] + 4 * q);
+          }
         } else {
           v[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
           u[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,8 +206,13 @@ __global__ void __launch_bounds__(256, MINB)
           if (q < nvec) {
             float4 du = make_float4(g * v[r][c].x, g * v[r][c].y, g * v[r][c].z, g * v[r][c].w);
             float4 dv = make_float4(g * u[r][c].x, g * u[r][c].y, g * u[r][c].z, g * u[r][c].w);
-            fps_red_add4(up[r] + 4 * q, du);   // worker-local user update
-            fps_red_add4(pp[r] + 4 * q, dv);   // the PUSH, fused with paramUpdate
+            if (HINT) {
+              fps_red_add4_hint(up[r] + 4 * q, du, pol_user);
+              fps_red_add4_hint(pp[r] + 4 * q, dv, pol_item);
+            } else {
+              fps_red_add4(up[r] + 4 * q, du);   // worker-local user update
+              fps_red_add4(pp[r] + 4 * q, dv);   // the PUSH, fused with paramUpdate
+            }
           }
         }
       }
@@ -214,13 +231,13 @@ __global__ void __launch_bounds__(256, MINB)
   if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
 }
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
   const int groups_per_block = threads / LPR;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT>, threads, 0);
+      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT>, threads, 0);
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
@@ -233,7 +250,7 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
   if (need < 1) need = 1;
   if (blocks > need) blocks = need;
-  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT><<<(int)blocks, threads, 0, stream>>>(a);
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT><<<(int)blocks, threads, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -251,6 +268,7 @@ static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStrea
   if (nvec <= 4) return launch_mf<IdT, 4, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
   if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 8, FMT>(a, max_inflight, num_sms, s);
   if (nvec <= 16) {
+    if (a.l2_hints) return launch_mf<IdT, 16, 1, 1, 8, FMT, 1>(a, max_inflight, num_sms, s);
     switch (v) {
       case 1: return launch_mf<IdT, 16, 1, 4, 3, FMT>(a, max_inflight, num_sms, s);
       case 3: return launch_mf<IdT, 16, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);

@@ -66,6 +66,8 @@ class MfArgsC(C.Structure):
         ("user_sharded", C.c_int),
         ("use_push_tab", C.c_int),
         ("push_tab", ShardTableC),
+        ("l2_hints", C.c_int),
+        ("pad2_", C.c_int),
     ]
 
 
@@ -227,7 +229,8 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  err_mode: int = 0, neg_rate: int = 0, num_items: int = 0, seed: int = 0,
                  step: int = 0, stats: Optional[torch.Tensor] = None,
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
-                 kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None) -> None:
+                 kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None,
+                 l2_hints: bool = False) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -267,8 +270,9 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     a.item_tab = item_tab
     if push_tab is not None:
         a.push_tab = push_tab; a.use_push_tab = 1
+    a.l2_hints = 1 if l2_hints else 0
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
-    if packed or push_tab is not None:
+    if packed or push_tab is not None or l2_hints:
         variant = "reg"
     rv = os.environ.get("FPS_MF_REG_VARIANT")
     if rv is not None:
@@ -328,6 +332,48 @@ def neg_sample(users: torch.Tensor, items: Optional[torch.Tensor], ratings: Opti
     _check(lib().fps_neg_sample(C.byref(a), 4 if packed else _id_bytes(users),
                                 sm_count(dev.index), _stream()), "neg_sample")
     _bump()
+    return ou, oi, orat
+
+
+class BucketArgsC(C.Structure):
+    """Mirror of ``struct BucketArgs`` (csrc/fps_bucket.cu)."""
+
+    _fields_ = [
+        ("users", C.c_void_p), ("items", C.c_void_p), ("ratings", C.c_void_p), ("n", C.c_longlong),
+        ("format", C.c_int), ("id_bytes", C.c_int), ("shift", C.c_int), ("n_buckets", C.c_int),
+        ("scratch", C.c_void_p), ("out_users", C.c_void_p), ("out_items", C.c_void_p),
+        ("out_ratings", C.c_void_p),
+    ]
+
+
+BUCKET_MAX = 64
+
+
+def bucket_by_item(users: torch.Tensor, items: Optional[torch.Tensor], ratings: Optional[torch.Tensor],
+                   shift: int, n_buckets: int, scratch: torch.Tensor):
+    """Reorder a micro-batch by ``item >> shift`` (L2 blocking of the item table, csrc/fps_bucket.cu).
+    ``items=None``: ``users`` holds packed64 records.  ``scratch``: int32 device tensor of
+    ``2 * BUCKET_MAX`` elements.  Returns the reordered ``(users, items, ratings)`` (new tensors)."""
+    _req(users, "users"); _req(scratch, "scratch", torch.int32)
+    packed = items is None
+    a = BucketArgsC()
+    a.users = users.data_ptr(); a.n = users.numel()
+    ou = torch.empty_like(users)
+    oi = orat = None
+    a.out_users = ou.data_ptr()
+    if packed:
+        if users.dtype != torch.int64:
+            raise TypeError("packed rating records must be an int64 tensor")
+        a.format = 1; a.id_bytes = 8
+    else:
+        _req(items, "items"); _req(ratings, "ratings", torch.float32)
+        oi, orat = torch.empty_like(items), torch.empty_like(ratings)
+        a.items = items.data_ptr(); a.ratings = ratings.data_ptr()
+        a.out_items = oi.data_ptr(); a.out_ratings = orat.data_ptr()
+        a.format = 0; a.id_bytes = _id_bytes(users)
+    a.shift = int(shift); a.n_buckets = int(n_buckets); a.scratch = scratch.data_ptr()
+    _check(lib().fps_bucket_by_item(C.byref(a), sm_count(users.device.index), _stream()), "bucket_by_item")
+    _bump(2)
     return ou, oi, orat
 
 

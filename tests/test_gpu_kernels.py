@@ -403,3 +403,58 @@ def test_replica_exchange_count_and_timer_triggers(dev):
     ids = torch.tensor([7], device=dev)
     torch.testing.assert_close(t.pull(ids)[0, :16], rc.cache[7, :16])  # ... reaches the master on flush
     t.close()
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_bucket_by_item_is_a_grouping_permutation(dev, packed):
+    from fps_b200.ops import native
+
+    n, n_items, shift = 100_003, 5000, 9                      # 10 buckets of 512 items
+    g = torch.Generator().manual_seed(11)
+    users = torch.randint(0, 1 << 20, (n,), generator=g, dtype=torch.int32).to(dev)
+    items = torch.randint(0, n_items, (n,), generator=g, dtype=torch.int32).to(dev)
+    ratings = torch.randint(0, 64, (n,), generator=g).float().to(dev)        # exact in fp16
+    scratch = torch.zeros(2 * native.BUCKET_MAX, dtype=torch.int32, device=dev)
+    nb = -(-n_items >> shift)
+    if packed:
+        rec = native.pack_ratings(users, items, ratings)
+        out, _, _ = native.bucket_by_item(rec, None, None, shift, nb, scratch)
+        assert torch.equal(torch.sort(out).values, torch.sort(rec).values)          # a permutation
+        b = ((out >> 16) & 0x3FFFFF) >> shift
+    else:
+        ou, oi, orat = native.bucket_by_item(users, items, ratings, shift, nb, scratch)
+        key_in = (users.long() << 40) | (items.long() << 8) | ratings.long()
+        key_out = (ou.long() << 40) | (oi.long() << 8) | orat.long()
+        assert torch.equal(torch.sort(key_out).values, torch.sort(key_in).values)
+        b = oi.long() >> shift
+    assert (b[1:] >= b[:-1]).all()                                                   # grouped by bucket
+    assert torch.equal(torch.bincount(b, minlength=nb), torch.bincount(items.long() >> shift, minlength=nb))
+
+
+def test_item_blocking_changes_order_not_result(dev):
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    g = torch.Generator().manual_seed(12)
+    nu, ni, n = 50_000, 20_000, 40_000
+    users = torch.randperm(nu, generator=g)[:n].to(torch.int32).to(dev)      # distinct users
+    items = torch.randint(0, ni, (n,), generator=g, dtype=torch.int32).to(dev)
+    ratings = torch.rand(n, generator=g).to(dev)
+    a = DeviceOnlineMF(nu, ni, 32, learning_rate=0.05, seed=5, item_blocking=False)
+    b = DeviceOnlineMF(nu, ni, 32, learning_rate=0.05, seed=5, item_blocking=True, block_bytes=256 << 10)
+    assert b.block_buckets > 4 and not a.item_blocking
+    for m in (a, b):
+        m.step(users, items, ratings)
+        m.step(native_pack(users, items, ratings))
+    torch.cuda.synchronize()
+    # items are shared between ratings of one batch (asynchronous updates): order changes the result
+    # only through which stale value a concurrent update reads -> compare loosely, users exactly-ish
+    torch.testing.assert_close(b.items.local, a.items.local, rtol=0, atol=2e-3)
+    torch.testing.assert_close(b.users, a.users, rtol=0, atol=2e-3)
+    assert b.stats[1].item() == a.stats[1].item() == 2 * n
+    a.close(); b.close()
+
+
+def native_pack(u, i, r):
+    from fps_b200.ops import native
+
+    return native.pack_ratings(u, i, r)
