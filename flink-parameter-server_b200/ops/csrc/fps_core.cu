@@ -641,6 +641,40 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Single-pass form of the two phases (default): with c = replica, b = base, v = master as read now,
+//   push   d = c - b  (REDG into the master row),      foreign  f = v - b  (REDG into the replica),
+//   base <- v + d     ("the master as this worker knows it, its own delta included").
+// Afterwards replica - base = (c + f + later local updates) - (v + d) = later local updates, the same
+// invariant as above, but every array is read once and base is written once: ~1.0 GB instead of ~1.8 GB
+// of local HBM traffic per exchange of a 256 MB table, and one launch instead of two.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+    fps_cache_exchange_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
+                              float* __restrict__ base, long long n_rows) {
+  const int lane = threadIdx.x & (LPR - 1);
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
+  const int stride = master.stride;
+  const int nvec = stride >> 2;
+  for (long long i = group; i < n_rows; i += n_groups) {
+    float* m = fps_row(master, i);
+    for (int q = lane; q < nvec; q += LPR) {
+      float* cp = cache + i * (long long)stride + 4 * q;
+      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
+      const float4 v = fps_ld_row4(m + 4 * q);   // owner's HBM (NVLink for remote shards)
+      const float4 c = fps_ld_row4(cp);
+      const float4 b = *bp;
+      const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
+      const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+      const bool has_d = d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f;
+      const bool has_f = f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f;
+      if (has_d) fps_red_add4(m + 4 * q, d);     // my updates since the last exchange
+      if (has_f) fps_red_add4(cp, f);            // the other workers' updates since the last exchange
+      if (has_d || has_f) *bp = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
+    }
+  }
+}
+
 #define FPS_SYNC_DISPATCH(KERNEL, ...)                                         \
   switch (lpr) {                                                               \
     case 1: KERNEL<1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
@@ -651,11 +685,18 @@ __global__ void __launch_bounds__(256)
     default: KERNEL<32><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;         \
   }
 
+static int g_cache_sync_variant = 0;  // 0: single-pass exchange, 1: two-phase (push_delta, refresh)
+extern "C" void fps_set_cache_sync_variant(int v) { g_cache_sync_variant = v; }
+
 extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* base, long long n_rows,
                               int num_sms, cudaStream_t stream) {
   if (n_rows <= 0) return 0;
   const int lpr = pick_lpr(master->stride >> 2);
   const int grid = row_grid(n_rows, lpr, num_sms);
+  if (g_cache_sync_variant == 0) {
+    FPS_SYNC_DISPATCH(fps_cache_exchange_kernel, *master, cache, base, n_rows)
+    return (int)cudaGetLastError();
+  }
   FPS_SYNC_DISPATCH(fps_cache_push_delta_kernel, *master, cache, base, n_rows)
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -433,14 +433,20 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
     return tc
 
 
+_CACHE_SYNC_TWO_PHASE = os.environ.get("FPS_CACHE_SYNC", "fused") == "2phase"
+
+
 def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor) -> None:
-    """Merge (replica - base) into the master shards, then refresh replica and base (2 launches)."""
+    """One delta exchange of a replica with its master shards: push ``replica - base``, fold the other
+    workers' ``master - base`` into the replica, ``base <- master + pushed delta`` (one streaming
+    kernel; ``FPS_CACHE_SYNC=2phase`` selects the original push_delta + refresh pair)."""
     _req(cache, "cache", torch.float32); _req(base, "base", torch.float32)
     assert cache.shape == base.shape and cache.shape[1] == master.stride
+    lib().fps_set_cache_sync_variant(1 if _CACHE_SYNC_TWO_PHASE else 0)
     _check(lib().fps_cache_sync(C.byref(master), C.c_void_p(cache.data_ptr()),
                                 C.c_void_p(base.data_ptr()), C.c_longlong(cache.shape[0]),
                                 sm_count(cache.device.index), _stream()), "cache_sync")
-    _bump(2)
+    _bump(2 if _CACHE_SYNC_TWO_PHASE else 1)
 
 
 def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: torch.Tensor) -> None:
