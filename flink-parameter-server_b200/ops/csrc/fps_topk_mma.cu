@@ -296,20 +296,33 @@ __global__ void __launch_bounds__(128 + 128 * MB, 1)
           // thread owns (row, split) for the whole kernel, so candidates go to a private segment of the
           // row's buffer with a register cursor: no atomics, no memory round trip in the epilogue
           // (a returning atomic per candidate / per chunk made pass 2 latency bound).
-          float cmax = -3.0e38f;
+          // The test is hierarchical (4 groups of 8 columns): when one lane of the warp has a candidate
+          // the whole warp walks the predicated append loop, so the loop is kept to the 8 columns of
+          // the group that actually reached theta instead of all 32.
+          float gmax[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
-          if (cmax >= th) {
+          for (int gi = 0; gi < 4; ++gi) {
+            float m = __uint_as_float(v[8 * gi]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int item = item0 + c0 + j;
-              const float sc = __uint_as_float(v[j]);
-              if (sc >= th && (full_tile || item < a.n_items)) {
-                if (n_cand < a.seg_cap) {
-                  seg_s[n_cand] = sc;
-                  seg_i[n_cand] = item;
+            for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * gi + j]));
+            gmax[gi] = m;
+          }
+          if (fmaxf(fmaxf(gmax[0], gmax[1]), fmaxf(gmax[2], gmax[3])) >= th) {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              if (gmax[gi] >= th) {
+#pragma unroll
+                for (int j = 8 * gi; j < 8 * gi + 8; ++j) {
+                  const int item = item0 + c0 + j;
+                  const float sc = __uint_as_float(v[j]);
+                  if (sc >= th && (full_tile || item < a.n_items)) {
+                    if (n_cand < a.seg_cap) {
+                      seg_s[n_cand] = sc;
+                      seg_i[n_cand] = item;
+                    }
+                    ++n_cand;
+                  }
                 }
-                ++n_cand;
               }
             }
           }

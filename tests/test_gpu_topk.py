@@ -139,3 +139,25 @@ def test_row_topk_sorted_matches_torch(dev, n, cap, K):
     assert (s[:, :7] == 1).all() and (s[:, 7:] == 0).all()
     assert torch.equal(i[0, :7], torch.arange(494, 501, dtype=torch.int32, device=dev))
     assert torch.equal(i[0, 7:], torch.arange(464, 477, dtype=torch.int32, device=dev))
+
+
+def test_topk_degenerate_queries_fall_back_to_brute_force(dev):
+    """An all-zero query ties every item at score 0: candidate segments overflow, theta cannot rise, and
+    the row must be answered by the brute-force path; ordinary rows of the same batch stay exact."""
+    from fps_b200.models.mf.device_topk import DeviceTopK
+
+    g = torch.Generator(device="cpu").manual_seed(8)
+    items = torch.randn(40000, 32, generator=g).to(dev)
+    q = torch.randn(300, 32, generator=g).to(dev)
+    q[7] = 0.0
+    q[123] = 0.0
+    for sort in (False, True):
+        tk = DeviceTopK(items, sort_by_length=sort)
+        sc, rows = tk.topk(25, q_local=q)
+        ref = torch.topk(DeviceTopK(items).scores(q_local=q), 25, dim=1)
+        assert torch.equal(sc, ref.values)
+        assert (sc[7] == 0).all() and (sc[123] == 0).all()
+        ok = torch.ones(300, dtype=torch.bool, device=dev); ok[7] = ok[123] = False
+        same = (rows == ref.indices) | (sc == torch.roll(sc, 1, 1)) | (sc == torch.roll(sc, -1, 1))
+        assert same[ok].all()
+        assert rows.min() >= 0 and rows.max() < 40000 and len(set(rows[7].tolist())) == 25
