@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from ...ops import native
+from ...utils.metrics import GLOBAL as METRICS
 from ...runtime.device_stream import DevicePrefetcher
 from ...store.replica_cache import ReplicaCache
 from ...store.sharded_table import ShardedTable
@@ -156,6 +157,7 @@ class DeviceOnlineMF:
                                 max_inflight_rows=self.pull_limit, kernel=self.kernel,
                                 l2_hints=self.l2_hints)
         self.step_no += 1
+        METRICS.inc("mf_ratings", users.numel())
 
     def make_graph_step(self, batch_size: int, packed: bool = True):
         """CUDA-graph a fixed-size micro-batch step for launch-bound streaming (small batches).

@@ -22,6 +22,7 @@ from typing import List, Optional
 import torch
 
 from ..ops import native
+from ..utils.metrics import GLOBAL as METRICS
 from .sharded_table import ShardedTable
 
 
@@ -80,6 +81,7 @@ class ReplicaCache:
         self._since_sync = 0
         self._last_sync = time.monotonic()
         self.exchanges += 1
+        METRICS.inc("replica_exchanges")
 
     def flush(self) -> None:
         """Push every pending local delta to the masters and make the current stream wait for it."""

@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from ..ops import native
+from ..utils.metrics import GLOBAL as METRICS
 from ..parallel.fabric import SymmetricHeap
 
 
@@ -101,12 +102,14 @@ class ShardedTable:
             out = torch.empty((ids.numel(), self.dim), dtype=torch.float32, device=ids.device)
         native.pull_gather(self.table_c, ids, out, touch=self.track_touched,
                            max_inflight_rows=pull_limit)
+        METRICS.inc("ps_pull_rows", ids.numel())
         return out
 
     def push(self, ids: torch.Tensor, deltas: torch.Tensor, scale: float = 1.0) -> None:
         """table[ids[i]] += scale * deltas[i] -- push fused with the additive paramUpdate (K2)."""
         native.push_add(self.table_c, ids, deltas, scale=scale, touch=self.track_touched,
                         nan_flag=self.nan_flag)
+        METRICS.inc("ps_push_rows", ids.numel())
 
     def pull_dot(self, ids: torch.Tensor, local_vectors: torch.Tensor) -> torch.Tensor:
         score = torch.empty(ids.numel(), dtype=torch.float32, device=ids.device)

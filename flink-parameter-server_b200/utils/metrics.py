@@ -84,4 +84,13 @@ class Counters:
             return dict(self._v)
 
 
+    def prometheus_text(self, prefix: str = "fps_b200_") -> str:
+        """Counters in the Prometheus text exposition format (one ``name value`` line each)."""
+        lines = []
+        for k, v in sorted(self.snapshot().items()):
+            name = prefix + "".join(ch if ch.isalnum() else "_" for ch in k)
+            lines.append(f"{name} {v:g}")
+        return "\n".join(lines) + ("\n" if lines else "")
+
+
 GLOBAL = Counters()

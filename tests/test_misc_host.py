@@ -97,3 +97,12 @@ def test_input_source_rate_replay():
     src2 = InputSource(None, 1, events=events, event_time=lambda e: e[0])
     src2.cancel()
     assert list(src2) == []
+
+
+def test_counters_prometheus_text():
+    from fps_b200.utils.metrics import Counters
+
+    c = Counters()
+    c.inc("ps_pull_rows", 10); c.inc("ps_pull_rows", 5); c.set("ring occupancy/max", 3)
+    text = c.prometheus_text()
+    assert "fps_b200_ps_pull_rows 15\n" in text and "fps_b200_ring_occupancy_max 3\n" in text
