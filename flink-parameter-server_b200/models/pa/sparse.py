@@ -69,8 +69,8 @@ class LegacySparseVector:
         return LegacySparseVector(dict(pairs), default)
 
     @staticmethod
-    def endOfFile(workerId: int, minusSourceId: int, default: float = 0.0) -> "LegacySparseVector":
-        return LegacySparseVector({workerId: float(minusSourceId)}, default)
+    def endOfFile(workerId: int, minusSourceId: int, default: float = 0.0) -> "EOFSign":
+        return EOFSign(workerId, minusSourceId)
 
     def getIndexes(self):
         return self.indexes.keys()
@@ -86,3 +86,21 @@ class LegacySparseVector:
 
     def __hash__(self) -> int:
         return hash(frozenset(self.indexes.items()))
+
+
+class EOFSign(LegacySparseVector):
+    """End-of-input marker of the legacy offline pipeline: an empty vector that carries the worker it is
+    addressed to and the (negated) id of the source that finished (entities/SparseVector.scala:13,42)."""
+
+    def __init__(self, workerId: int, minusSourceId: int):
+        super().__init__({}, 0.0)
+        self.workerId, self.minusSourceId = int(workerId), int(minusSourceId)
+
+    def __eq__(self, o) -> bool:
+        return isinstance(o, EOFSign) and (self.workerId, self.minusSourceId) == (o.workerId, o.minusSourceId)
+
+    def __hash__(self) -> int:
+        return hash(("EOFSign", self.workerId, self.minusSourceId))
+
+    def __repr__(self) -> str:
+        return f"EOFSign(workerId={self.workerId}, minusSourceId={self.minusSourceId})"

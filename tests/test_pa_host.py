@@ -8,7 +8,7 @@ from fps_b200.api import Left, Right
 from fps_b200.models.pa.algorithms import (PassiveAggressiveBinaryAlgorithm, PassiveAggressiveCostBased,
                                            PassiveAggressiveOneVersusAll)
 from fps_b200.models.pa.ps import transformBinary, transformMulticlass, transformMulticlassWithLongId
-from fps_b200.models.pa.sparse import LegacySparseVector, SparseVector
+from fps_b200.models.pa.sparse import EOFSign, LegacySparseVector, SparseVector
 
 
 def test_sparse_vector_and_legacy_builders():
@@ -16,7 +16,9 @@ def test_sparse_vector_and_legacy_builders():
     assert v.indices.tolist() == [1, 5] and v.dot({1: 1.0, 5: 0.5}) == 4.0 and v.norm_sq() == 13.0
     a = LegacySparseVector.build([(1, 2.0), (3, 4.0)])
     assert a == LegacySparseVector({1: 2.0, 3: 4.0}) and a.get(9) == 0.0
-    assert LegacySparseVector.endOfFile(2, -7).getValues() == {2: -7.0}
+    eof = LegacySparseVector.endOfFile(2, -7)              # entities/SparseVector.scala:13,42
+    assert isinstance(eof, EOFSign) and (eof.workerId, eof.minusSourceId) == (2, -7) and eof.getValues() == {}
+    assert eof == EOFSign(2, -7) and eof != EOFSign(2, -8)
 
 
 def test_binary_pa_variants():
