@@ -147,7 +147,8 @@ class DeviceOnlineMF:
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
-                                max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints)
+                                max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints,
+                                reserve_ctas=self.replica.reserve())
             self.replica.after_step()
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,

@@ -51,7 +51,8 @@ class DeviceSkipGram:
         native.mf_sgd_fused(centers, contexts, self._ones, tin, 1, tout, self.lr,
                             err_mode=ERR_LOGISTIC, neg_rate=self.negative, num_items=self.vocab,
                             seed=self.seed, step=self.step_no, stats=self.stats, nan_flag=self.nan_flag,
-                            kernel="reg")
+                            kernel="reg",
+                            reserve_ctas=(self.rep_in.reserve() + self.rep_out.reserve()) if self.rep_in else 0)
         if self.rep_in:
             self.rep_in.after_step(); self.rep_out.after_step()
         self.step_no += 1

@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(256, MINB)
   if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
 }
 
+static int g_mf_reserve = 0;  // CTA slots per SM left free for a concurrently running exchange kernel
+extern "C" void fps_set_mf_reserve(int v) { g_mf_reserve = v < 0 ? 0 : v; }
+
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
@@ -238,6 +241,7 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(
       &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT>, threads, 0);
+  occ -= g_mf_reserve;  // leave slots for the background replica exchange (see fps_cache_sync)
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ;
   // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
@@ -656,21 +660,39 @@ __global__ void __launch_bounds__(256)
   const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
   const int stride = master.stride;
   const int nvec = stride >> 2;
-  for (long long i = group; i < n_rows; i += n_groups) {
-    float* m = fps_row(master, i);
+  // two rows per step: all six loads (two of them possibly over NVLink) are issued before any use, so
+  // the kernel keeps its bandwidth when it is confined to one or two CTAs per SM next to training
+  for (long long i0 = group; i0 < n_rows; i0 += 2 * n_groups) {
+    const long long i1 = i0 + n_groups;
+    const bool two = i1 < n_rows;
+    float* m0 = fps_row(master, i0);
+    float* m1 = two ? fps_row(master, i1) : m0;
     for (int q = lane; q < nvec; q += LPR) {
-      float* cp = cache + i * (long long)stride + 4 * q;
-      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
-      const float4 v = fps_ld_row4(m + 4 * q);   // owner's HBM (NVLink for remote shards)
-      const float4 c = fps_ld_row4(cp);
-      const float4 b = *bp;
-      const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
-      const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
-      const bool has_d = d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f;
-      const bool has_f = f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f;
-      if (has_d) fps_red_add4(m + 4 * q, d);     // my updates since the last exchange
-      if (has_f) fps_red_add4(cp, f);            // the other workers' updates since the last exchange
-      if (has_d || has_f) *bp = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
+      float* cp0 = cache + i0 * (long long)stride + 4 * q;
+      float* cp1 = cache + (two ? i1 : i0) * (long long)stride + 4 * q;
+      float4* bp0 = reinterpret_cast<float4*>(base + i0 * (long long)stride + 4 * q);
+      float4* bp1 = reinterpret_cast<float4*>(base + (two ? i1 : i0) * (long long)stride + 4 * q);
+      const float4 v0 = fps_ld_row4(m0 + 4 * q);   // owner's HBM (NVLink for remote shards)
+      const float4 v1 = fps_ld_row4(m1 + 4 * q);
+      const float4 c0 = fps_ld_row4(cp0);
+      const float4 c1 = fps_ld_row4(cp1);
+      const float4 b0 = *bp0;
+      const float4 b1 = *bp1;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        const float4 v = r ? v1 : v0, c = r ? c1 : c0, b = r ? b1 : b0;
+        float* m = (r ? m1 : m0) + 4 * q;
+        float* cp = r ? cp1 : cp0;
+        float4* bp = r ? bp1 : bp0;
+        const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
+        const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
+        const bool has_d = d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f;
+        const bool has_f = f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f;
+        if (has_d) fps_red_add4(m, d);     // my updates since the last exchange
+        if (has_f) fps_red_add4(cp, f);    // the other workers' updates since the last exchange
+        if (has_d || has_f) *bp = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
+      }
     }
   }
 }
@@ -688,11 +710,15 @@ __global__ void __launch_bounds__(256)
 static int g_cache_sync_variant = 0;  // 0: single-pass exchange, 1: two-phase (push_delta, refresh)
 extern "C" void fps_set_cache_sync_variant(int v) { g_cache_sync_variant = v; }
 
+// ctas_per_sm > 0 confines the exchange to that many CTAs per SM (grid-stride over the rows) so that it
+// runs NEXT TO a training kernel that left the same number of slots free (fps_set_mf_reserve), instead
+// of queueing behind / in front of a kernel that fills every SM.
 extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* base, long long n_rows,
-                              int num_sms, cudaStream_t stream) {
+                              int num_sms, int ctas_per_sm, cudaStream_t stream) {
   if (n_rows <= 0) return 0;
   const int lpr = pick_lpr(master->stride >> 2);
-  const int grid = row_grid(n_rows, lpr, num_sms);
+  int grid = row_grid(n_rows, lpr, num_sms);
+  if (ctas_per_sm > 0 && grid > num_sms * ctas_per_sm) grid = num_sms * ctas_per_sm;
   if (g_cache_sync_variant == 0) {
     FPS_SYNC_DISPATCH(fps_cache_exchange_kernel, *master, cache, base, n_rows)
     return (int)cudaGetLastError();

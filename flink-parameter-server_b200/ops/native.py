@@ -230,7 +230,7 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  step: int = 0, stats: Optional[torch.Tensor] = None,
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
                  kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None,
-                 l2_hints: bool = False) -> None:
+                 l2_hints: bool = False, reserve_ctas: int = 0) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -274,6 +274,7 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
     if packed or push_tab is not None or l2_hints:
         variant = "reg"
+    lib().fps_set_mf_reserve(int(reserve_ctas))
     rv = os.environ.get("FPS_MF_REG_VARIANT")
     if rv is not None:
         lib().fps_set_mf_reg_variant(int(rv))
@@ -436,7 +437,7 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
 _CACHE_SYNC_TWO_PHASE = os.environ.get("FPS_CACHE_SYNC", "fused") == "2phase"
 
 
-def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor) -> None:
+def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor, ctas_per_sm: int = 0) -> None:
     """One delta exchange of a replica with its master shards: push ``replica - base``, fold the other
     workers' ``master - base`` into the replica, ``base <- master + pushed delta`` (one streaming
     kernel; ``FPS_CACHE_SYNC=2phase`` selects the original push_delta + refresh pair)."""
@@ -445,7 +446,7 @@ def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor) -> 
     lib().fps_set_cache_sync_variant(1 if _CACHE_SYNC_TWO_PHASE else 0)
     _check(lib().fps_cache_sync(C.byref(master), C.c_void_p(cache.data_ptr()),
                                 C.c_void_p(base.data_ptr()), C.c_longlong(cache.shape[0]),
-                                sm_count(cache.device.index), _stream()), "cache_sync")
+                                sm_count(cache.device.index), int(ctas_per_sm), _stream()), "cache_sync")
     _bump(2 if _CACHE_SYNC_TWO_PHASE else 1)
 
 
