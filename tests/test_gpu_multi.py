@@ -21,3 +21,15 @@ def test_two_rank_fabric_and_fused_step():
            os.path.join(REPO, "tests", "mp_device_check.py")]
     r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MP_DEVICE_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.multigpu
+def test_two_rank_distributed_topk():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29618",
+           os.path.join(REPO, "tests", "mp_topk_check.py")]
+    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_TOPK_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -161,3 +161,21 @@ def test_topk_degenerate_queries_fall_back_to_brute_force(dev):
         same = (rows == ref.indices) | (sc == torch.roll(sc, 1, 1)) | (sc == torch.roll(sc, -1, 1))
         assert same[ok].all()
         assert rows.min() >= 0 and rows.max() < 40000 and len(set(rows[7].tolist())) == 25
+
+
+def test_distributed_topk_single_rank_maps_to_global_ids(dev):
+    from fps_b200.models.mf.device_topk import DistributedTopK
+    from fps_b200.store.sharded_table import ShardedTable
+
+    users = ShardedTable(2000, 32, seed=4, init_range=(-1, 1))
+    g = torch.Generator(device="cpu").manual_seed(9)
+    items = torch.randn(3000, 32, generator=g).to(dev)
+    gids = (torch.arange(3000, device=dev) * 7 + 3)
+    q = torch.randint(0, 2000, (150,), generator=g).to(dev)
+    sc, ids = DistributedTopK(users, items, gids).topk(q, 15, workerK=15)
+    exact = users.pull(q) @ items.T
+    ref = torch.topk(exact, 15, dim=1)
+    overlap = (ids[:, :, None] == gids[ref.indices][:, None, :]).any(-1).float().mean().item()
+    assert overlap > 0.97 and ((ids - 3) % 7 == 0).all()
+    torch.testing.assert_close(sc, ref.values, rtol=2e-2, atol=2e-2)
+    users.close()
