@@ -174,10 +174,16 @@ def _broadcast_ratings(src, workerParallelism: int) -> DataStream:
 def psTopKGenerator(src, model, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: float = 0.01,
                     userMemory: int = 0, K: int = 100, workerK: int = 75, bucketSize: int = 100,
                     pruningAlgorithm: LEMPPruningStrategy = COORD(), pullLimit: int = 1600,
-                    workerParallelism: int = 4, psParallelism: int = 4, iterationWaitTime: float = 10000):
+                    workerParallelism: int = 4, psParallelism: int = 4, iterationWaitTime: float = 10000,
+                    backend: str = "local", **device_kw):
     """``model``: stream of ``Left((itemId, (len, vec)))`` (to workers) / ``Right((userId, (len, vec)))``
     (to the PS) -- note the reference's Either orientation is kept.  Returns
-    ``[(itemId, timestamp, [(score, itemId)])]`` per rating."""
+    ``[(itemId, timestamp, [(score, itemId)])]`` per rating.  ``backend="device"``: tcgen05 scoring
+    against a length-sorted item table (``models/mf/device_api.py::ps_topk_generator_device``)."""
+    if backend == "device":
+        from .device_api import ps_topk_generator_device
+
+        return ps_topk_generator_device(src, model, K=K, workerK=workerK, userMemory=userMemory, **device_kw)
     worker = addPullLimiter(PSTopKGeneratorWorker(workerK, bucketSize, workerParallelism, pruningAlgorithm),
                             pullLimit)
     psLogic = SimplePSLogic(lambda _i: INVALID_PARAM, lambda _old, new: new)
@@ -269,9 +275,17 @@ def psOnlineLearnerAndGenerator(src, numFactors: int = 10, rangeMin: float = -0.
                                 pruningAlgorithm: LEMPPruningStrategy = LI(5, 2.5), pullLimit: int = 500,
                                 workerParallelism: int = 4, psParallelism: int = 4,
                                 iterationWaitTime: float = 10000, seed: Optional[int] = None,
-                                plain_residual: bool = False):
+                                plain_residual: bool = False, backend: str = "local", **device_kw):
     """Returns ``[(userId, itemId, timestamp, [(score, itemId)])]`` -- one top-K per rating, computed
-    BEFORE the model is updated with that rating (prequential evaluation)."""
+    BEFORE the model is updated with that rating (prequential evaluation).  ``backend="device"``:
+    ``models/mf/device_api.py::ps_online_learner_and_generator_device``."""
+    if backend == "device":
+        from .device_api import ps_online_learner_and_generator_device
+
+        return ps_online_learner_and_generator_device(
+            src, numFactors=numFactors, rangeMin=rangeMin, rangeMax=rangeMax, learningRate=learningRate,
+            negativeSampleRate=negativeSampleRate, userMemory=userMemory, K=K, pullLimit=pullLimit,
+            seed=seed or 0, plain_residual=plain_residual, **device_kw)
     initDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax, seed)
     worker = addPullLimiter(
         PSOnlineMatrixFactorizationAndTopKGeneratorWorker(

@@ -179,3 +179,45 @@ def test_distributed_topk_single_rank_maps_to_global_ids(dev):
     assert overlap > 0.97 and ((ids - 3) % 7 == 0).all()
     torch.testing.assert_close(sc, ref.values, rtol=2e-2, atol=2e-2)
     users.close()
+
+
+def test_ps_topk_generator_and_online_learner_device_backends(dev):
+    """Reference-shaped entry points on the device tier: same lists as the host tier (LEMP scan) for a
+    pre-trained model; unknown users get an empty list; the online learner is prequential."""
+    import numpy as np
+
+    from fps_b200.api import Left, Right
+    from fps_b200.models.mf.common import Rating, attachLength
+    from fps_b200.models.mf.topk import psOnlineLearnerAndGenerator, psTopKGenerator
+
+    rng = np.random.RandomState(0)
+    k, n_items, n_users = 8, 300, 40
+    items = {i: rng.randn(k) * (0.5 + rng.rand()) for i in range(n_items)}
+    users = {u: rng.randn(k) for u in range(0, n_users, 2)}            # odd users are unknown
+    model = [Left((i, attachLength(v))) for i, v in items.items()] + \
+            [Right((u, attachLength(v))) for u, v in users.items()]
+    queries = [Rating(int(u), int(rng.randint(n_items)), 1.0, t) for t, u in enumerate(rng.randint(0, n_users, 60))]
+    host = psTopKGenerator(queries, model, K=10, workerK=10, workerParallelism=2, psParallelism=2,
+                           iterationWaitTime=200)
+    devr = psTopKGenerator(queries, model, K=10, workerK=10, backend="device")
+    assert len(devr) == len(queries)
+    by_ts = {ts: topk for (_item, ts, topk) in host}
+    for (item, ts, topk), q in zip(devr, queries):
+        assert item == q.item and ts == q.timestamp
+        if q.user % 2 == 1:
+            assert topk == []
+            continue
+        want = by_ts[ts]
+        assert len(set(i for _, i in topk) & set(i for _, i in want)) >= 9          # same items (TF32 near-ties) ...
+        np.testing.assert_allclose([s for s, _ in topk], [s for s, _ in want], rtol=5e-3, atol=5e-3)  # TF32 scores
+    # online learner + generator: one list per rating, lists exclude nothing for memory 0, model trains
+    ratings = [Rating(int(rng.randint(30)), int(rng.randint(50)), 1.0, t) for t in range(500)]
+    out = psOnlineLearnerAndGenerator(ratings, numFactors=8, K=5, userMemory=0, backend="device",
+                                      learningRate=0.1, rangeMin=0.05, rangeMax=0.3, batch_size=100,
+                                      plain_residual=True)
+    assert len(out) == 500 and all(len(t) == 5 for (_u, _i, _ts, t) in out)
+    assert [(u, i, ts) for (u, i, ts, _t) in out] == [(r.user, r.item, r.timestamp) for r in ratings]
+    pred = out.model.predict(torch.tensor([r.user for r in ratings[:100]], device=dev, dtype=torch.int32),
+                             torch.tensor([r.item for r in ratings[:100]], device=dev, dtype=torch.int32))
+    assert pred.mean().item() > 0.45                                   # trained towards rating 1 from ~0.25
+    out.model.close()
