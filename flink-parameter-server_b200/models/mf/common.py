@@ -13,7 +13,7 @@ import math
 import random
 import threading
 from dataclasses import dataclass
-from typing import Callable, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 

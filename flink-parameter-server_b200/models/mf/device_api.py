@@ -9,7 +9,7 @@ users touched and ``Right((itemId, vector))`` for the local shard's items (model
 """
 from __future__ import annotations
 
-from typing import Iterable, Iterator, List, Optional, Sequence
+from typing import Iterator, List, Optional, Sequence
 
 import torch
 

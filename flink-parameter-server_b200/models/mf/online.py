@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import random
 from collections import deque
-from typing import Dict, Iterable, Optional
+from typing import Dict, Optional
 
 import numpy as np
 

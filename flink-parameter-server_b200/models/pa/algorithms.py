@@ -12,7 +12,7 @@ A *model* is what the worker assembled from the pulled parameters: for binary a
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, Iterable, List, Tuple
+from typing import Callable, Dict, List, Tuple
 
 import numpy as np
 

@@ -17,7 +17,7 @@ from __future__ import annotations
 import random
 import threading
 from collections import deque
-from typing import Dict, Iterable, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 from ...api import CtorFork, WorkerLogic
 from ...limiter import addBlockingPullLimiter

@@ -13,7 +13,7 @@ Device equivalents: models/sketch/device.py + ops/csrc/fps_sketch.cu (packed bit
 from __future__ import annotations
 
 import math
-from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Sequence, Tuple
 
 from ...api import Left, ParameterServerLogic, Right, WorkerLogic
 from ...limiter import addPullLimiter

@@ -2,7 +2,7 @@
 from __future__ import annotations
 
 import math
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 
 def dotProduct(u: Sequence[int], v: Sequence[int]) -> int:

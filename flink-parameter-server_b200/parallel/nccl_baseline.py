@@ -12,7 +12,7 @@ the gloo backend and CPU tensors the same class is the multi-process CPU plumbin
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Sequence, Tuple
+from typing import Iterable, Optional, Sequence
 
 import torch
 import torch.distributed as dist

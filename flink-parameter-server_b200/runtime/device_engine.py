@@ -16,7 +16,7 @@ for touched ids (``*WithClose`` semantics) when ``dump_model=True``.
 """
 from __future__ import annotations
 
-from typing import Any, Iterable, List, Optional
+from typing import Any, Iterable, List
 
 import torch
 

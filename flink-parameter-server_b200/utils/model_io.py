@@ -7,7 +7,7 @@ The loaded ``(id, value)`` pairs feed ``transformWithModelLoad`` / ``ShardedTabl
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, Iterator, List, Tuple
+from typing import Callable, Iterable, Iterator, Tuple
 
 import numpy as np
 

@@ -12,7 +12,7 @@ from __future__ import annotations
 import contextlib
 import json
 import os
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 
