@@ -46,30 +46,56 @@ def clone_logic(obj: Any) -> Any:
 
 
 class _Activity:
-    """In-flight accounting for quiescence detection."""
+    """In-flight accounting for quiescence detection, without a shared lock on the message path.
+
+    Every thread that sends or finishes messages owns a slot ``[sent, done, last_event]`` that only it
+    writes (a single lock here turned into a convoy: all worker / PS threads serialised on it and the
+    engine ran at ~13 K messages/s).  The controller sums the ``done`` counters FIRST and the ``sent``
+    counters afterwards: ``done == sent`` then implies that at the first instant nothing was in flight
+    and nothing was sent in between (every message is sent before it is done)."""
 
     def __init__(self):
-        self.lock = threading.Lock()
-        self.inflight = 0
-        self.last_event = time.monotonic()
+        self.lock = threading.Lock()          # slot registration, sources_open and error only
+        self._local = threading.local()
+        self._slots: List[list] = []
         self.sources_open = 0
         self.error: Optional[BaseException] = None
+        self._t0 = time.monotonic()
+
+    def _slot(self) -> list:
+        s = getattr(self._local, "slot", None)
+        if s is None:
+            s = [0, 0, time.monotonic()]
+            self._local.slot = s
+            with self.lock:
+                self._slots.append(s)
+        return s
 
     def add(self, n: int = 1) -> None:
-        with self.lock:
-            self.inflight += n
-            self.last_event = time.monotonic()
+        s = self._slot()
+        s[0] += n
+        s[2] = time.monotonic()
 
     def done(self, n: int = 1) -> None:
-        with self.lock:
-            self.inflight -= n
-            self.last_event = time.monotonic()
+        s = self._slot()
+        s[1] += n
+        s[2] = time.monotonic()
+
+    def touch(self) -> None:
+        self._slot()[2] = time.monotonic()
+
+    @property
+    def inflight(self) -> int:
+        slots = list(self._slots)
+        done = sum(s[1] for s in slots)
+        sent = sum(s[0] for s in slots)
+        return sent - done
 
     def idle_for(self) -> float:
-        with self.lock:
-            if self.inflight != 0 or self.sources_open != 0:
-                return 0.0
-            return time.monotonic() - self.last_event
+        if self.sources_open != 0 or self.inflight != 0:
+            return 0.0
+        last = max([s[2] for s in list(self._slots)], default=self._t0)
+        return time.monotonic() - max(last, self._t0)
 
 
 class MessagingPSClient(ParameterServerClient):
@@ -228,9 +254,9 @@ class LocalEngine:
             except BaseException as e:  # noqa: BLE001
                 fail(e)
             finally:
+                act.touch()
                 with act.lock:
                     act.sources_open -= 1
-                    act.last_event = time.monotonic()
 
         threads = [threading.Thread(target=worker_loop, args=(i,), daemon=True, name=f"fps-worker-{i}")
                    for i in range(self.wP)]
