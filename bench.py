@@ -59,7 +59,7 @@ def parse():
                    help="parity: the reference's e = sigmoid(r - u.v) (SGDUpdater.scala:8; always positive, so "
                         "the squared error drifts up by design); plain: e = r - u.v (textbook SGD, loss falls)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
-                   help="fused MF kernel variant (default: tma pipeline)")
+                   help="fused MF kernel variant (default: reg = register-staged loads at full occupancy)")
     return p.parse_args()
 
 
