@@ -86,9 +86,8 @@ class _Activity:
 
     @property
     def inflight(self) -> int:
-        slots = list(self._slots)
-        done = sum(s[1] for s in slots)
-        sent = sum(s[0] for s in slots)
+        done = sum(s[1] for s in list(self._slots))
+        sent = sum(s[0] for s in list(self._slots))   # later, possibly larger snapshot: never under-counts
         return sent - done
 
     def idle_for(self) -> float:
