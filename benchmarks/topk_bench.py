@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--K", type=int, default=100)
     ap.add_argument("--skew", type=float, default=0.0,
                     help="> 0: log-normal item lengths with this sigma (popularity skew) instead of U[0.05, 2.05)")
+    ap.add_argument("--pass1-fraction", type=float, default=0.0,
+                    help="> 0: also time DeviceTopK(pass1_fraction=f) (theta from a prefix of the tiles)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -62,6 +64,13 @@ def main():
     tkp = DeviceTopK(items.local, sort_by_length=True)       # LEMP LENGTH bound at tile granularity
     ms_pruned = t_ms(lambda: tkp.topk(a.K, q_ids=q, q_table=users), iters=5, warm=2)
     p1, p2 = tkp.last_tiles_scored
+    ms_frac = None
+    if a.pass1_fraction > 0:
+        tkf = DeviceTopK(items.local, pass1_fraction=a.pass1_fraction)
+        ms_frac = t_ms(lambda: tkf.topk(a.K, q_ids=q, q_table=users), iters=5, warm=2)
+        ref_s, _ = tk.topk(a.K, q_ids=q, q_table=users)
+        got_s, _ = tkf.topk(a.K, q_ids=q, q_table=users)
+        assert torch.equal(ref_s, got_s), "pass1_fraction changed the result"
     for name, t in (("plain", tk), ("pruned", tkp)):       # per-stage breakdown (synchronising trace)
         t.trace = []; t._t0 = None
         t.topk(a.K, q_ids=q, q_table=users)
@@ -71,6 +80,7 @@ def main():
     print(json.dumps({"queries": a.queries, "items": a.items, "factors": a.factors, "K": a.K,
                       "pass1_ms": ms_pass1, "pass1_tf32_TFLOPs": flops / ms_pass1 / 1e9,
                       "topk_total_ms": ms_total, "queries_per_s": a.queries / ms_total * 1e3,
+                      "pass1_fraction": a.pass1_fraction, "pass1_fraction_total_ms": ms_frac,
                       "length_pruned_total_ms": ms_pruned, "tiles": tkp.n_tiles, "tiles_pass1": p1,
                       "tiles_pass2": p2, "skew": a.skew,
                       "torch_matmul_topk_ms": ms_torch, "speedup_vs_torch": ms_torch / ms_total}))

@@ -34,7 +34,8 @@ class DeviceTopK:
 
     LENGTH_SLACK = 1.004  # TF32 products may exceed the fp32 Cauchy-Schwarz bound by ~2^-10 relative
 
-    def __init__(self, items: torch.Tensor, max_batch_bytes: int = 512 << 20, sort_by_length: bool = False):
+    def __init__(self, items: torch.Tensor, max_batch_bytes: int = 512 << 20, sort_by_length: bool = False,
+                 pass1_fraction: Optional[float] = None):
         if items.dim() != 2 or items.shape[1] % 4 != 0:
             raise ValueError("items must be [n_items, stride] with stride % 4 == 0")
         self.perm = None
@@ -47,6 +48,10 @@ class DeviceTopK:
         self.n_items, self.stride = items.shape
         self.n_tiles = (self.n_items + native.TOPK_TILE - 1) // native.TOPK_TILE
         self.max_batch_bytes = max_batch_bytes
+        # experimental (not yet measured): compute theta from the first `pass1_fraction` of the tiles only.
+        # The K-th largest tile maximum of ANY subset of tiles is still a valid lower bound (K distinct
+        # items reach it), just a weaker one: pass 1 shrinks to that fraction, pass 2 keeps more candidates.
+        self.pass1_fraction = pass1_fraction
         self._last = (0, None, None)
         self.trace = None                 # set to [] to collect (stage, ms) pairs (synchronising!)
         self._t0 = None
@@ -117,7 +122,16 @@ class DeviceTopK:
             lim1 = lim2 = None
             p1 = self.n_tiles
             prune = self.perm is not None and self.n_tiles >= 16 and max(Kp, self.n_tiles // 8) < self.n_tiles
-            if not prune:
+            frac_tiles = 0
+            if not prune and self.pass1_fraction:
+                frac_tiles = max(Kp, int(self.n_tiles * float(self.pass1_fraction)))
+            if not prune and 0 < frac_tiles < self.n_tiles:
+                p1 = frac_tiles
+                tile_max = torch.full((n, self.n_tiles), -3.0e38, dtype=torch.float32, device=dev)
+                first = torch.full((1,), p1, dtype=torch.int32, device=dev)
+                native.topk_mma(self.items, 1, tile_max=tile_max, tile_limit=first, **kw)
+                self._mark("pass1-prefix")
+            elif not prune:
                 tile_max = torch.empty((n, self.n_tiles), dtype=torch.float32, device=dev)
                 native.topk_mma(self.items, 1, tile_max=tile_max, **kw)
                 self._mark("pass1")
