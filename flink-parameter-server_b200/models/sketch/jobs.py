@@ -32,6 +32,28 @@ def _ps_only(result) -> List[Any]:
     return result.ps_outputs()
 
 
+def _device_train(kind: str, src, numHashes: int, arraySize: int = 0, capacity=None, group=None,
+                  chunk: int = 65536) -> List[Any]:
+    """``backend="device"`` of the push-only train jobs: the same ``(tweetId, [words])`` stream updates a
+    :class:`~fps_b200.models.sketch.device.DeviceSketch` (one-sided ``red.or / red.add / red.min`` pushes)
+    and the ``close()`` dump has the host jobs' shape.  Integer tweet ids; the hash family is the device
+    one (``hashing.hash64``), not the reference's murmur3 / xxHash, so bit positions differ from the host
+    tier while the sketch semantics (and the estimates) are the same.  In a multi-rank job every rank
+    feeds its partition of the stream and gets the dump of its own shard."""
+    from .device import DeviceSketch
+
+    recs = [(int(r[0]), list(r[1])) for r in (src.collect() if hasattr(src, "collect") else src)]
+    if capacity is None:
+        capacity = max(1, len({w for _t, ws in recs for w in ws}))
+    sk = DeviceSketch(kind, int(capacity), numHashes, arraySize, group=group)
+    try:
+        for a in range(0, len(recs), chunk):
+            sk.update(recs[a:a + chunk])
+        return sk.model()
+    finally:
+        sk.close()
+
+
 # =============================================================================================
 # Bloom filter
 # =============================================================================================
@@ -69,8 +91,10 @@ class _BloomWorker(WorkerLogic):
 
 
 def bloomFilter(src, arraySize: int, numHashes: int, workerParallelism: int, psParallelism: int,
-                iterationWaitTime: float = 10000) -> List[Tuple[int, frozenset]]:
+                iterationWaitTime: float = 10000, backend: str = "local", **device_kw) -> List[Tuple[int, frozenset]]:
     """Train: stream of ``(tweetId, [words])`` -> ``[(wordHash, bitset)]`` (BloomFilter.scala:32-98)."""
+    if backend == "device":
+        return _device_train("bloom", src, numHashes, arraySize, **device_kw)
     return _ps_only(transform(src, _BloomWorker(arraySize, numHashes), BloomPSLogic(),
                               workerParallelism, psParallelism, iterationWaitTime))
 
@@ -308,8 +332,11 @@ class _ToWWorker(WorkerLogic):
     onPullRecv = _unsupported
 
 
-def tugOfWar(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000):
+def tugOfWar(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000,
+             backend: str = "local", **device_kw):
     """(TugOfWar.scala:17-82) -> ``[(wordHash, int counters[numHashes])]``."""
+    if backend == "device":
+        return _device_train("tow", src, numHashes, **device_kw)
     return _ps_only(transform(src, _ToWWorker(numHashes), BitSetBasedPSLogic(numHashes),
                               workerParallelism, psParallelism, iterationWaitTime))
 
@@ -487,8 +514,11 @@ class _MinHashWorker(WorkerLogic):
     onPullRecv = _unsupported
 
 
-def minhash(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000):
+def minhash(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000,
+            backend: str = "local", **device_kw):
     """(MinHash.scala:15-74) -> ``[(wordHash, [argmin tweetId per slot])]``."""
+    if backend == "device":
+        return _device_train("minhash", src, numHashes, **device_kw)
     return _ps_only(transform(src, _MinHashWorker(numHashes), SendHashPSLogic(numHashes),
                               workerParallelism, psParallelism, iterationWaitTime))
 
