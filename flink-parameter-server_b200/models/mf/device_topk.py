@@ -102,6 +102,8 @@ class DeviceTopK:
         item_rows index the caller's item table."""
         n_q = q_ids.numel() if q_ids is not None else q_local.shape[0]
         Kp = min(K, self.n_items)
+        if Kp > 2048:
+            raise ValueError("DeviceTopK supports K <= 2048 (shared-memory sort buffer of fps_row_topk)")
         T = native.TOPK_TILE
         dev = self.items.device
         # candidate buffer: a few x K per query is typical (worst case K*128 and more with ties); an
