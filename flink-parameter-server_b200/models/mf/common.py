@@ -25,8 +25,7 @@ UserId = int
 ItemId = int
 
 
-class FactorIsNotANumberException(ArithmeticError):
-    """A NaN appeared in a factor vector (Vector.scala:78-80)."""
+from ...errors import FactorIsNotANumberException  # noqa: E402,F401  (re-exported; Vector.scala:78-80)
 
 
 def vectorLengthSqr(v: Vector) -> float:

@@ -22,6 +22,7 @@ from typing import Iterable, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
+from ...errors import FactorIsNotANumberException
 from ...ops import native
 from ...utils.metrics import GLOBAL as METRICS
 from ...runtime.device_stream import DevicePrefetcher
@@ -266,7 +267,7 @@ class DeviceOnlineMF:
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:
-            raise FloatingPointError("non-finite SGD update (FactorIsNotANumberException)")
+            raise FactorIsNotANumberException("non-finite SGD update")
 
     def barrier(self) -> None:
         self.flush()

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from ...api import Left, Right
+from ...errors import FactorIsNotANumberException
 from ...ops import native
 from ...runtime.stream import ResultStream, as_stream
 from ...store.sharded_table import ShardedTable
@@ -98,7 +99,7 @@ class DevicePassiveAggressive:
 
     def check_finite(self):
         if int(self.nan_flag.item()):
-            raise FloatingPointError("non-finite passive-aggressive update")
+            raise FactorIsNotANumberException("non-finite passive-aggressive update")
 
     def close(self):
         self.table.close()

@@ -16,6 +16,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from ..errors import FactorIsNotANumberException
 from ..ops import native
 from ..store.replica_cache import ReplicaCache
 from ..store.sharded_table import ShardedTable
@@ -75,7 +76,7 @@ class DeviceSkipGram:
 
     def check_finite(self):
         if int(self.nan_flag.item()):
-            raise FloatingPointError("non-finite skip-gram update")
+            raise FactorIsNotANumberException("non-finite skip-gram update")
 
     def barrier(self):
         self.flush()

@@ -19,6 +19,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ..errors import FactorIsNotANumberException
 from ..ops import native
 from ..utils.metrics import GLOBAL as METRICS
 from ..parallel.fabric import SymmetricHeap
@@ -119,7 +120,7 @@ class ShardedTable:
     def check_finite(self) -> None:
         """Raise like ``FactorIsNotANumberException`` (Vector.scala:78-80) if a NaN was pushed."""
         if int(self.nan_flag.item()) != 0:
-            raise FloatingPointError("non-finite value pushed to the parameter server")
+            raise FactorIsNotANumberException("non-finite value pushed to the parameter server")
 
     # -- model export / import (PS output at close; transformWithModelLoad) -------------------
     def dump_local(self, only_touched: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
