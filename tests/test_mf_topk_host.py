@@ -75,3 +75,25 @@ def test_online_learner_and_generator_emits_one_topk_per_rating():
     assert len(out) == len(ratings)
     assert all(len(topk) <= 5 for *_x, topk in out)
     assert any(len(topk) > 0 for *_x, topk in out[50:])
+
+
+def test_device_api_seen_filter_matches_collect_topk_semantics():
+    """`_seen_filter` (used by the device backends) == the sequential part of CollectTopKFromEachWorker:
+    drop items the user rated within the last `memory` events, then remember the rated item."""
+    from fps_b200.api import Left
+    from fps_b200.models.mf.common import Rating
+    from fps_b200.models.mf.device_api import _seen_filter
+    from fps_b200.models.mf.topk import CollectTopKFromEachWorker
+
+    cand = [(float(10 - i), i) for i in range(10)]                       # items 0..9, best first
+    events = [Rating(1, 0, 1.0, 0), Rating(1, 1, 1.0, 1), Rating(2, 0, 1.0, 2), Rating(1, 2, 1.0, 3),
+              Rating(1, 3, 1.0, 4)]
+    for memory in (0, 1, 2, -1):
+        rows = [(e.user, e.item, e.timestamp, list(cand)) for e in events]
+        got = _seen_filter(rows, 4, memory)
+        ref = CollectTopKFromEachWorker(4, memory, 1)
+        want = []
+        for rid, e in enumerate(events):
+            want += ref.flatMap(Left((e.enrich(0, rid), list(cand))))
+        assert got == want, memory
+    assert [i for _, i in _seen_filter([(1, 0, 0, list(cand)), (1, 5, 1, list(cand))], 3, 5)[1][3]] == [1, 2, 3]
