@@ -189,38 +189,49 @@ class LocalEngine:
 
         def worker_loop(i: int) -> None:
             logic, recv, client = w_logic[i], w_recv[i], clients[i]
+            inbox_get, on_answer_msg, done = w_inbox[i].get, recv.onPullAnswerRecv, act.done
+
+            def on_answer(a: PullAnswer) -> None:
+                logic.onPullRecv(a.paramId, a.param, client)
+
             try:
                 if self.call_worker_open:
                     logic.open()
+                on_recv = logic.onRecv          # bound after open(): a logic may rebind its callbacks there
                 while True:
-                    kind, payload = w_inbox[i].get()
+                    kind, payload = inbox_get()
                     if kind == _STOP:
                         break
                     try:
                         if kind == _DATA:
-                            logic.onRecv(payload, client)
+                            on_recv(payload, client)
                         else:
-                            recv.onPullAnswerRecv(
-                                payload, lambda a: logic.onPullRecv(a.paramId, a.param, client))
+                            on_answer_msg(payload, on_answer)
                     finally:
-                        act.done()
+                        done()
             except BaseException as e:  # noqa: BLE001
                 fail(e)
 
         def ps_loop(j: int) -> None:
             logic, recv, server = p_logic[j], p_recv[j], servers[j]
+            inbox_get, on_msg, done = ps_inbox[j].get, recv.onWorkerMsg, act.done
+
+            def on_pull(id, widx) -> None:
+                logic.onPullRecv(id, widx, server)
+
+            def on_push(id, delta) -> None:
+                logic.onPushRecv(id, delta, server)
+
             try:
                 logic.open({}, RuntimeContext(j, self.psP))
                 while True:
-                    kind, payload = ps_inbox[j].get()
+                    kind, payload = inbox_get()
                     if kind == _STOP:
                         break
                     try:
-                        recv.onWorkerMsg(payload,
-                                         lambda id, widx: logic.onPullRecv(id, widx, server),
-                                         lambda id, delta: logic.onPushRecv(id, delta, server))
+                        on_msg(payload, on_pull, on_push)
                     finally:
-                        act.done()
+                        done()
             except BaseException as e:  # noqa: BLE001
                 fail(e)
 
