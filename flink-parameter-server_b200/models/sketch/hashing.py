@@ -24,7 +24,11 @@ def _rotl32(x: int, r: int) -> int:
 
 
 def murmur3_32(data, seed: int = 0) -> int:
-    """MurmurHash3 x86_32 of a str (utf-8) / bytes; returns a signed 32-bit int like the JVM."""
+    """MurmurHash3 x86_32 of a str (utf-8) / bytes; returns a signed 32-bit int like the JVM.
+    Integers are hashed through their decimal string (tweet ids arrive as strings in the reference's
+    readers; numeric ids hash to the same value as their string form)."""
+    if isinstance(data, int):
+        data = str(data)
     if isinstance(data, str):
         data = data.encode("utf-8")
     c1, c2 = 0xCC9E2D51, 0x1B873593
