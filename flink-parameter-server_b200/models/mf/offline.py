@@ -90,6 +90,11 @@ def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: fl
                 psParallelism: int = 1, iterationWaitTime: float = 10000, seed: Optional[int] = None,
                 plain_residual: bool = False, shuffle: bool = False, backend: str = "local",
                 **device_kw):
+    if backend == "native":
+        from .native_api import ps_mf_native
+
+        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
+                            psParallelism, seed or 0, plain_residual, epochs=iterations)
     if backend == "device":
         from .device_api import ps_offline_mf_device
 

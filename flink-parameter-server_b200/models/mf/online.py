@@ -108,7 +108,14 @@ def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: flo
                pullLimit: int = 1600, workerParallelism: int = 1, psParallelism: int = 1,
                iterationWaitTime: float = 10000, seed: Optional[int] = None,
                plain_residual: bool = False, backend: str = "local", **device_kw):
-    """Returns the stream of ``Left((userId, userVector))`` / ``Right((itemId, itemVector))``."""
+    """Returns the stream of ``Left((userId, userVector))`` / ``Right((itemId, itemVector))``.
+    ``backend="local"``: arbitrary-logic Python engine; ``"native"``: the same protocol on the C++ host
+    engine (threads + SPSC rings, ``ops/csrc/fps_host.cpp``); ``"device"``: fused B200 kernels."""
+    if backend == "native":
+        from .native_api import ps_mf_native
+
+        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
+                            psParallelism, seed or 0, plain_residual, epochs=1)
     if backend == "device":
         from .device_api import ps_online_mf_device
 

@@ -7,7 +7,11 @@
 //    (user:26 | item:22 | fp16 rating:16) straight into per-worker (pinned) buffers.
 //  * key interner: opaque 64-bit keys (e.g. String.hashCode of a word, or a hashed string id) to dense
 //    slot ids for the device tables.
+//  * native asynchronous MF engine: worker and server threads exchanging pull / answer / push messages over
+//    lock-free SPSC rings (the CPU backend of psOnlineMF / psOfflineMF at native speed, see the end).
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -111,6 +115,193 @@ int fps_interner_keys(void* p, int64_t* out) {
   std::lock_guard<std::mutex> g(in->mu);
   std::memcpy(out, in->keys.data(), in->keys.size() * sizeof(int64_t));
   return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Native host engine for asynchronous SGD matrix factorisation (the CPU backend of psOnlineMF /
+// psOfflineMF at native speed).  It runs the reference's protocol, not a shortcut:
+//   * W worker threads own the users (user % W), S server threads own the item vectors (item % S)
+//     (PSOnlineMatrixFactorization.scala:58-64);
+//   * per rating: Pull(item) -> PullAnswer(item, vector) -> SGD delta -> local user update ->
+//     Push(item, delta) -> paramUpdate = vector sum (PSOnlineMatrixFactorizationWorker.scala:42-89);
+//   * at most `pull_limit` unanswered pulls per worker (WorkerLogic.addPullLimiter, WL:196-250);
+//   * messages travel through single-producer / single-consumer rings, one per (worker, server) pair and
+//     direction, so delivery is FIFO per pair like Flink's channels and answers are matched to ratings by
+//     order (the reference's per-item rating queues rely on the same property).
+// Ring capacities make sends non-blocking by construction: a worker has at most `pull_limit` pulls and
+// `pull_limit` pushes in flight towards one server, a server at most `pull_limit` answers towards one worker.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int MF_MAX_K = 128;
+
+struct MfMsg {
+  int32_t kind;  // 0 pull, 1 push, 2 answer
+  int32_t id;
+  float v[MF_MAX_K];
+};
+
+struct MfRing {  // SPSC
+  std::vector<MfMsg> buf;
+  size_t cap = 0;
+  alignas(64) std::atomic<size_t> head{0};  // next to pop
+  alignas(64) std::atomic<size_t> tail{0};  // next to push
+  void init(size_t c) { cap = c; buf.resize(c); }
+  MfMsg* begin_push() {
+    const size_t t = tail.load(std::memory_order_relaxed);
+    if (t - head.load(std::memory_order_acquire) >= cap) return nullptr;
+    return &buf[t % cap];
+  }
+  void end_push() { tail.store(tail.load(std::memory_order_relaxed) + 1, std::memory_order_release); }
+  MfMsg* front() {
+    const size_t h = head.load(std::memory_order_relaxed);
+    if (h == tail.load(std::memory_order_acquire)) return nullptr;
+    return &buf[h % cap];
+  }
+  void pop() { head.store(head.load(std::memory_order_relaxed) + 1, std::memory_order_release); }
+};
+
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// deterministic "init on first pull": a pure function of (seed, id, column)
+static inline float init_value(uint64_t seed, int64_t id, int j, float lo, float hi) {
+  const uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)id * 0x100000001B3ull + (uint64_t)j));
+  return lo + (hi - lo) * (float)((h >> 40) * (1.0 / 16777216.0));
+}
+
+}  // namespace
+
+extern "C" {
+
+// users/items/ratings: the whole stream (every worker filters its own users, order preserved).
+// user_table [num_users, k], item_table [num_items, k] are initialised here (init_value) and trained in
+// place; *_touched are set for ids that occurred.  err_mode 0: e = sigmoid(r - u.v) (SGDUpdater.scala:8),
+// 1: e = r - u.v.  Returns 0, or -1 for bad arguments, -2 if a non-finite update appeared.
+int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* ratings, int64_t n,
+                      int32_t workers, int32_t servers, int32_t k, float lr, int32_t err_mode, float lo,
+                      float hi, uint64_t seed, int32_t epochs, int32_t pull_limit, float* user_table,
+                      int64_t num_users, float* item_table, int64_t num_items, uint8_t* user_touched,
+                      uint8_t* item_touched, double* sum_sq_err) {
+  if (workers < 1 || servers < 1 || k < 1 || k > MF_MAX_K || pull_limit < 1 || epochs < 1) return -1;
+  for (int64_t i = 0; i < n; ++i)
+    if (users[i] < 0 || users[i] >= num_users || items[i] < 0 || items[i] >= num_items) return -1;
+  for (int64_t u = 0; u < num_users; ++u)
+    for (int j = 0; j < k; ++j) user_table[u * k + j] = init_value(seed * 2 + 2, u, j, lo, hi);
+  for (int64_t it = 0; it < num_items; ++it)
+    for (int j = 0; j < k; ++j) item_table[it * k + j] = init_value(seed * 2 + 1, it, j, lo, hi);
+
+  const size_t cap_w2s = 2 * (size_t)pull_limit + 8, cap_s2w = (size_t)pull_limit + 8;
+  std::vector<MfRing> w2s((size_t)workers * servers), s2w((size_t)workers * servers);
+  for (auto& r : w2s) r.init(cap_w2s);
+  for (auto& r : s2w) r.init(cap_s2w);
+  std::atomic<int> workers_done{0};
+  std::atomic<int> bad{0};
+  std::vector<double> sq(workers, 0.0);
+
+  auto worker = [&](int w) {
+    std::vector<int64_t> mine;
+    for (int64_t i = 0; i < n; ++i)
+      if (users[i] % workers == w) mine.push_back(i);
+    std::vector<std::vector<int64_t>> pend(servers);  // FIFO of rating indices awaiting an answer, per server
+    std::vector<size_t> pend_head(servers, 0);
+    double acc = 0.0;
+    for (int ep = 0; ep < epochs; ++ep) {
+      size_t next = 0;
+      int outstanding = 0;
+      while (next < mine.size() || outstanding > 0) {
+        bool progressed = false;
+        while (next < mine.size() && outstanding < pull_limit) {  // the pull limiter
+          const int64_t idx = mine[next];
+          const int s = items[idx] % servers;
+          MfMsg* m = w2s[(size_t)w * servers + s].begin_push();
+          if (m == nullptr) break;
+          m->kind = 0; m->id = items[idx];
+          w2s[(size_t)w * servers + s].end_push();
+          pend[s].push_back(idx);
+          ++next; ++outstanding; progressed = true;
+        }
+        for (int s = 0; s < servers; ++s) {
+          MfRing& in = s2w[(size_t)w * servers + s];
+          while (MfMsg* a = in.front()) {
+            MfRing& out = w2s[(size_t)w * servers + s];
+            MfMsg* p = out.begin_push();
+            if (p == nullptr) break;  // cannot happen by the capacity argument; stay safe
+            const int64_t idx = pend[s][pend_head[s]++];
+            float* u = user_table + (int64_t)users[idx] * k;
+            float dot = 0.f;
+            for (int j = 0; j < k; ++j) dot += u[j] * a->v[j];
+            const float resid = ratings[idx] - dot;
+            const float e = err_mode == 0 ? 1.f / (1.f + std::exp(-resid)) : resid;
+            const float g = lr * e;
+            if (!(std::fabs(g) <= 3.0e38f)) bad = 1;
+            acc += (double)resid * resid;
+            p->kind = 1; p->id = a->id;
+            for (int j = 0; j < k; ++j) {
+              p->v[j] = g * u[j];        // item delta (uses the user vector BEFORE its update, like delta())
+              u[j] += g * a->v[j];       // worker-local user update
+            }
+            out.end_push();
+            in.pop();
+            user_touched[users[idx]] = 1;
+            --outstanding; progressed = true;
+          }
+        }
+        if (!progressed) std::this_thread::yield();
+      }
+      for (int s = 0; s < servers; ++s) { pend[s].clear(); pend_head[s] = 0; }
+    }
+    sq[w] = acc;
+    workers_done.fetch_add(1, std::memory_order_release);
+  };
+
+  auto server = [&](int s) {
+    while (true) {
+      bool progressed = false;
+      const bool all_done = workers_done.load(std::memory_order_acquire) == workers;
+      for (int w = 0; w < workers; ++w) {
+        MfRing& in = w2s[(size_t)w * servers + s];
+        while (MfMsg* m = in.front()) {
+          float* row = item_table + (int64_t)m->id * k;
+          if (m->kind == 0) {
+            MfRing& out = s2w[(size_t)w * servers + s];
+            MfMsg* a = out.begin_push();
+            if (a == nullptr) break;  // answer ring full: the worker will drain it
+            a->kind = 2; a->id = m->id;
+            std::memcpy(a->v, row, sizeof(float) * k);
+            out.end_push();
+            item_touched[m->id] = 1;
+          } else {
+            for (int j = 0; j < k; ++j) row[j] += m->v[j];  // paramUpdate = vectorSum
+          }
+          in.pop();
+          progressed = true;
+        }
+      }
+      if (!progressed) {
+        if (all_done) {
+          bool empty = true;
+          for (int w = 0; w < workers; ++w) empty = empty && w2s[(size_t)w * servers + s].front() == nullptr;
+          if (empty) break;
+        }
+        std::this_thread::yield();
+      }
+    }
+  };
+
+  std::vector<std::thread> th;
+  for (int s = 0; s < servers; ++s) th.emplace_back(server, s);
+  for (int w = 0; w < workers; ++w) th.emplace_back(worker, w);
+  for (auto& t : th) t.join();
+  double total = 0.0;
+  for (double x : sq) total += x;
+  if (sum_sq_err != nullptr) *sum_sq_err = total;
+  return bad.load() ? -2 : 0;
 }
 
 }  // extern "C"

@@ -76,3 +76,37 @@ class NativeInterner:
             lib().fps_interner_free(self._p)
         except Exception:
             pass
+
+
+def mf_train(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, num_users: int, num_items: int,
+             num_factors: int = 10, range_min: float = -0.01, range_max: float = 0.01,
+             learning_rate: float = 0.01, workers: int = 4, servers: int = 4, pull_limit: int = 1600,
+             epochs: int = 1, seed: int = 0, plain_residual: bool = False):
+    """Asynchronous SGD matrix factorisation on the native host engine (``fps_host_mf_train``): worker and
+    server *threads* exchanging pull / answer / push messages over lock-free SPSC rings with a pull limiter
+    -- the reference's protocol at native speed, no GPU.  Returns ``(user_table, item_table, user_touched,
+    item_touched, sum_sq_err)`` as numpy arrays."""
+    u = users.to(torch.int32).contiguous(); i = items.to(torch.int32).contiguous()
+    r = ratings.to(torch.float32).contiguous()
+    n = int(u.numel())
+    k = int(num_factors)
+    ut = np.empty((int(num_users), k), dtype=np.float32)
+    it = np.empty((int(num_items), k), dtype=np.float32)
+    utouch = np.zeros(int(num_users), dtype=np.uint8)
+    itouch = np.zeros(int(num_items), dtype=np.uint8)
+    sse = C.c_double(0.0)
+    rc = lib().fps_host_mf_train(
+        C.c_void_p(u.data_ptr()), C.c_void_p(i.data_ptr()), C.c_void_p(r.data_ptr()), C.c_int64(n),
+        C.c_int32(workers), C.c_int32(servers), C.c_int32(k), C.c_float(learning_rate),
+        C.c_int32(1 if plain_residual else 0), C.c_float(range_min), C.c_float(range_max),
+        C.c_uint64(seed & (2**64 - 1)), C.c_int32(epochs), C.c_int32(pull_limit),
+        ut.ctypes.data_as(C.c_void_p), C.c_int64(num_users), it.ctypes.data_as(C.c_void_p),
+        C.c_int64(num_items), utouch.ctypes.data_as(C.c_void_p), itouch.ctypes.data_as(C.c_void_p),
+        C.byref(sse))
+    if rc == -2:
+        from ..errors import FactorIsNotANumberException
+
+        raise FactorIsNotANumberException("non-finite SGD update in the native host engine")
+    if rc != 0:
+        raise ValueError("bad arguments for the native MF engine (ids out of range, k > 128, ...)")
+    return ut, it, utouch.astype(bool), itouch.astype(bool), float(sse.value)

@@ -1,0 +1,110 @@
+"""Native host engine (C++ threads + SPSC rings) for asynchronous MF: exact in sequential mode, passes the
+reference's quality gate (T/matrix/factorization/PSOfflineMatrixFactorizationTest.scala:55-103) in parallel."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from fps_b200.models.mf.common import Rating
+from fps_b200.models.mf.offline import psOfflineMF
+from fps_b200.models.mf.online import psOnlineMF
+from fps_b200.ops import host
+
+M64 = (1 << 64) - 1
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    return x ^ (x >> 31)
+
+
+def _init(seed, id_, j, lo, hi):
+    h = _splitmix64(seed ^ _splitmix64((id_ * 0x100000001B3 + j) & M64))
+    return np.float32(lo) + np.float32(hi - lo) * np.float32((h >> 40) * (1.0 / 16777216.0))
+
+
+def test_sequential_mode_equals_a_plain_sgd_loop():
+    """1 worker, 1 server, pullLimit 1 => no concurrency => bit-for-bit the textbook loop."""
+    rnd = random.Random(0)
+    nu, ni, k, n = 12, 9, 6, 200
+    u = [rnd.randrange(nu) for _ in range(n)]
+    i = [rnd.randrange(ni) for _ in range(n)]
+    r = [rnd.random() for _ in range(n)]
+    for plain in (False, True):
+        ut, it, utc, itc, sse = host.mf_train(torch.tensor(u), torch.tensor(i), torch.tensor(r), nu, ni, k, -0.1, 0.1,
+                                             0.05, workers=1, servers=1, pull_limit=1, epochs=2, seed=3,
+                                             plain_residual=plain)
+        U = np.array([[_init(3 * 2 + 2, a, j, -0.1, 0.1) for j in range(k)] for a in range(nu)], dtype=np.float32)
+        V = np.array([[_init(3 * 2 + 1, a, j, -0.1, 0.1) for j in range(k)] for a in range(ni)], dtype=np.float32)
+        for _ep in range(2):
+            for a, b, c in zip(u, i, r):
+                v = V[b].copy()
+                dot = np.float32(0)
+                for j in range(k):
+                    dot = np.float32(dot + U[a, j] * v[j])
+                resid = np.float32(np.float32(c) - dot)
+                e = resid if plain else np.float32(1.0) / (np.float32(1.0) + np.exp(-resid, dtype=np.float32))
+                g = np.float32(np.float32(0.05) * e)
+                delta = (g * U[a]).astype(np.float32)
+                U[a] = (U[a] + g * v).astype(np.float32)
+                V[b] = (V[b] + delta).astype(np.float32)
+        np.testing.assert_allclose(ut, U, rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(it, V, rtol=2e-6, atol=1e-7)
+        assert utc.sum() == len(set(u)) and itc.sum() == len(set(i))
+
+
+def test_parallel_engine_passes_the_reference_quality_gate():
+    rnd = random.Random(47)
+    seen, ratings = set(), []
+    while len(ratings) < 100:
+        a, b = rnd.randrange(20), rnd.randrange(15)
+        if (a, b) not in seen:
+            seen.add((a, b))
+            ratings.append(Rating(a, b, rnd.random(), 0))
+    out = psOfflineMF(ratings, numFactors=15, rangeMin=0.0, rangeMax=0.3, learningRate=0.05, iterations=25,
+                      pullLimit=10, workerParallelism=4, psParallelism=4, seed=1, backend="native",
+                      plain_residual=True)             # same configuration as the host-tier gate (test_mf_host.py)
+    U = dict(out.worker_outputs()); V = dict(out.ps_outputs())
+    assert set(U) == {r.user for r in ratings} and set(V) == {r.item for r in ratings}
+    rmse = np.sqrt(np.mean([(float(np.dot(U[r.user], V[r.item])) - r.rating) ** 2 for r in ratings]))
+    assert rmse <= 0.5, rmse
+
+
+def test_online_backend_native_learns_and_validates_arguments():
+    g = torch.Generator().manual_seed(1)
+    nu, ni, n = 300, 100, 60000
+    P, Q = torch.rand(nu, 3, generator=g), torch.rand(ni, 3, generator=g)
+    u = torch.randint(0, nu, (n,), generator=g); i = torch.randint(0, ni, (n,), generator=g)
+    r = (P[u] * Q[i]).sum(1) / 3
+    recs = [Rating(int(a), int(b), float(c), 0) for a, b, c in zip(u, i, r)]
+    out = psOnlineMF(recs, numFactors=8, rangeMin=-0.1, rangeMax=0.1, learningRate=0.05, pullLimit=32,
+                     workerParallelism=3, psParallelism=2, seed=2, backend="native", plain_residual=True)
+    U = dict(out.worker_outputs()); V = dict(out.ps_outputs())
+    pred = np.array([np.dot(U[int(a)], V[int(b)]) for a, b in zip(u[-5000:], i[-5000:])])
+    assert np.sqrt(np.mean((pred - r[-5000:].numpy()) ** 2)) < 0.12
+    with pytest.raises(ValueError):
+        host.mf_train(torch.tensor([5]), torch.tensor([0]), torch.tensor([1.0]), 3, 3)      # user id out of range
+    with pytest.raises(ValueError):
+        host.mf_train(torch.tensor([0]), torch.tensor([0]), torch.tensor([1.0]), 3, 3, num_factors=500)
+
+
+def test_native_engine_is_race_free_under_thread_sanitizer(tmp_path):
+    """Race detection (absent in the reference): randomised worker / server / pull-limit
+    configurations of the native engine under ThreadSanitizer."""
+    import os
+    import shutil
+    import subprocess
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")],
+                           input="int main(){return 0;}", text=True, capture_output=True)
+    if probe.returncode != 0:
+        pytest.skip("g++ has no ThreadSanitizer runtime")
+    r = subprocess.run(["bash", os.path.join(repo, "scripts", "tsan_host.sh")], cwd=repo, capture_output=True,
+                       text=True, timeout=900, env={**os.environ, "TMPDIR": str(tmp_path)})
+    assert r.returncode == 0 and "tsan: clean" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
