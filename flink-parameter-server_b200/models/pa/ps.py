@@ -117,6 +117,38 @@ def _transform_generic(model, init, add, inputSource, workerParallelism, psParal
                              iterationWaitTime)
 
 
+def _transform_binary_native(model, inputSource, workerParallelism, psParallelism, algo, pullLimit, featureCount,
+                             rangePartitioning):
+    """``backend="native"``: the same job on the C++ host engine (worker / server threads over SPSC rings,
+    ``ops/csrc/fps_host.cpp::fps_host_pa_binary``)."""
+    import numpy as np
+
+    from ...ops import host
+    from ...runtime.stream import ResultStream, as_stream
+    from .device import algo_to_device
+
+    name, C, _ = algo_to_device(algo)
+    recs = as_stream(inputSource).collect()
+    weights = np.zeros(int(featureCount), dtype=np.float32)
+    if model is not None:
+        for fid, w in as_stream(model).collect():
+            weights[int(fid)] = w
+    row_ptr, cols, vals, labels = [0], [], [], []
+    for d in recs:
+        vec = d.value[0] if d.is_left else d.value[1]
+        cols.extend(vec.indices.tolist()); vals.extend(vec.values.tolist())
+        row_ptr.append(len(cols))
+        labels.append((1 if d.value[1] else -1) if d.is_left else 0)
+    pred, weights, touched = host.pa_binary(row_ptr, cols, vals, labels, int(featureCount), name, C,
+                                            workers=workerParallelism, servers=psParallelism,
+                                            pull_limit=max(1, int(pullLimit)),
+                                            range_partitioning=bool(rangePartitioning), weights=weights)
+    out = [Left((d.value[1], bool(p))) for d, p in zip(recs, pred) if not d.is_left]
+    keep = touched | (weights != 0)
+    out += [Right((int(f), float(weights[f]))) for f in np.nonzero(keep)[0]]
+    return ResultStream(out)
+
+
 def transformBinary(model=None):
     """``transformBinary(model)(inputSource, workerParallelism, psParallelism, algo, pullLimit,
     featureCount, rangePartitioning, iterationWaitTime)``; input records are
@@ -125,6 +157,9 @@ def transformBinary(model=None):
 
     def run(inputSource, workerParallelism, psParallelism, passiveAggressiveMethod, pullLimit,
             featureCount, rangePartitioning=False, iterationWaitTime=10000, backend="local", **kw):
+        if backend == "native":
+            return _transform_binary_native(model, inputSource, workerParallelism, psParallelism,
+                                            passiveAggressiveMethod, pullLimit, featureCount, rangePartitioning)
         if backend == "device":
             from .device import transform_binary_device
 

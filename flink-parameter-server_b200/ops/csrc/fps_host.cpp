@@ -305,3 +305,169 @@ int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* r
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Native host engine for the binary passive-aggressive classifiers (PA / PA-I / PA-II;
+// PassiveAggressiveParameterServer.scala:283-340, PassiveAggressiveBinaryAlgorithm.scala:44-112):
+// one scalar weight per feature on the server threads (hash or range partitioned), worker threads take
+// the examples round-robin, pull every active feature of an example (bounded by the pull limiter),
+// and once all answers are in either predict (unlabelled) or push tau*y*x_i per feature.
+// Same SPSC-ring transport as the MF engine above.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct PaMsg {
+  int32_t kind;  // 0 pull, 1 push, 2 answer
+  int32_t id;
+  float v;
+  int32_t pad;
+};
+
+struct PaRing {
+  std::vector<PaMsg> buf;
+  size_t cap = 0;
+  alignas(64) std::atomic<size_t> head{0};
+  alignas(64) std::atomic<size_t> tail{0};
+  void init(size_t c) { cap = c; buf.resize(c); }
+  bool push(const PaMsg& m) {
+    const size_t t = tail.load(std::memory_order_relaxed);
+    if (t - head.load(std::memory_order_acquire) >= cap) return false;
+    buf[t % cap] = m;
+    tail.store(t + 1, std::memory_order_release);
+    return true;
+  }
+  bool pop(PaMsg& m) {
+    const size_t h = head.load(std::memory_order_relaxed);
+    if (h == tail.load(std::memory_order_acquire)) return false;
+    m = buf[h % cap];
+    head.store(h + 1, std::memory_order_release);
+    return true;
+  }
+  bool empty() { return head.load(std::memory_order_relaxed) == tail.load(std::memory_order_acquire); }
+};
+
+}  // namespace
+
+extern "C" {
+
+// CSR examples (row_ptr[n+1], cols, vals); labels: +1 / -1, or 0 = unlabelled (predict only).
+// algo: 0 PA, 1 PA-I, 2 PA-II; weights[feature_count] in/out (initial model); pred[n] out (1 / 0);
+// touched[feature_count] out.  range_partition: contiguous feature ranges per server
+// (RangePSLogicWithClose.scala:51-62) instead of feature % servers.
+int fps_host_pa_binary(const int64_t* row_ptr, const int32_t* cols, const float* vals, const int32_t* labels,
+                       int64_t n, int64_t feature_count, int32_t algo, float C, int32_t workers,
+                       int32_t servers, int32_t pull_limit, int32_t range_partition, float* weights,
+                       int32_t* pred, uint8_t* touched) {
+  if (workers < 1 || servers < 1 || pull_limit < 1 || feature_count < 1 || algo < 0 || algo > 2) return -1;
+  for (int64_t j = 0; j < row_ptr[n]; ++j)
+    if (cols[j] < 0 || cols[j] >= feature_count) return -1;
+  const int64_t div = (feature_count + servers - 1) / servers;
+  auto owner = [&](int32_t f) -> int {
+    if (!range_partition) return f % servers;
+    const int64_t s = f / div;
+    return (int)(s < servers ? s : servers - 1);
+  };
+  std::vector<PaRing> w2s((size_t)workers * servers), s2w((size_t)workers * servers);
+  for (auto& r : w2s) r.init(2 * (size_t)pull_limit + 64);
+  for (auto& r : s2w) r.init((size_t)pull_limit + 8);
+  std::atomic<int> workers_done{0};
+  std::atomic<int> bad{0};
+
+  auto drain_answers = [&](int w, std::vector<std::vector<int64_t>>& pend, std::vector<size_t>& pend_head,
+                           std::vector<float>& wbuf, int64_t& received) {
+    bool any = false;
+    PaMsg a;
+    for (int s = 0; s < servers; ++s)
+      while (s2w[(size_t)w * servers + s].pop(a)) {
+        wbuf[pend[s][pend_head[s]++]] = a.v;
+        ++received;
+        any = true;
+      }
+    return any;
+  };
+
+  auto worker = [&](int w) {
+    std::vector<std::vector<int64_t>> pend(servers);
+    std::vector<size_t> pend_head(servers, 0);
+    std::vector<float> wbuf;
+    for (int64_t ex = w; ex < n; ex += workers) {
+      const int64_t b = row_ptr[ex], m = row_ptr[ex + 1] - b;
+      wbuf.assign((size_t)m, 0.f);
+      for (int s = 0; s < servers; ++s) { pend[s].clear(); pend_head[s] = 0; }
+      int64_t issued = 0, received = 0;
+      while (received < m) {
+        bool progressed = false;
+        while (issued < m && issued - received < pull_limit) {  // the pull limiter
+          const int s = owner(cols[b + issued]);
+          if (!w2s[(size_t)w * servers + s].push(PaMsg{0, cols[b + issued], 0.f, 0})) break;
+          pend[s].push_back(issued);
+          ++issued;
+          progressed = true;
+        }
+        progressed |= drain_answers(w, pend, pend_head, wbuf, received);
+        if (!progressed) std::this_thread::yield();
+      }
+      float dot = 0.f, nsq = 0.f;
+      for (int64_t j = 0; j < m; ++j) { dot += wbuf[j] * vals[b + j]; nsq += vals[b + j] * vals[b + j]; }
+      pred[ex] = dot > 0.f ? 1 : 0;
+      const int y = labels[ex];
+      if (y == 0 || m == 0 || !(nsq > 0.f)) continue;
+      const float loss = std::max(0.f, 1.f - (float)y * dot);
+      float tau;
+      if (algo == 0) tau = loss / nsq;
+      else if (algo == 1) tau = std::min(C, loss / nsq);
+      else tau = loss / (nsq + 1.f / (2.f * C));
+      if (tau == 0.f) continue;
+      if (!(std::fabs(tau) <= 3.0e38f)) bad = 1;
+      for (int64_t j = 0; j < m; ++j) {
+        const int s = owner(cols[b + j]);
+        const PaMsg p{1, cols[b + j], tau * (float)y * vals[b + j], 0};
+        while (!w2s[(size_t)w * servers + s].push(p)) std::this_thread::yield();  // server always drains
+      }
+    }
+    workers_done.fetch_add(1, std::memory_order_release);
+  };
+
+  auto server = [&](int s) {
+    PaMsg m;
+    while (true) {
+      bool progressed = false;
+      const bool all_done = workers_done.load(std::memory_order_acquire) == workers;
+      for (int w = 0; w < workers; ++w) {
+        PaRing& in = w2s[(size_t)w * servers + s];
+        PaRing& out = s2w[(size_t)w * servers + s];
+        while (true) {
+          const size_t h = in.head.load(std::memory_order_relaxed);
+          if (h == in.tail.load(std::memory_order_acquire)) break;
+          const PaMsg& peek = in.buf[h % in.cap];
+          if (peek.kind == 0) {
+            if (!out.push(PaMsg{2, peek.id, weights[peek.id], 0})) break;  // answer ring full: retry later
+            touched[peek.id] = 1;
+          } else {
+            weights[peek.id] += peek.v;  // paramUpdate = +
+            touched[peek.id] = 1;
+          }
+          in.head.store(h + 1, std::memory_order_release);
+          progressed = true;
+        }
+      }
+      if (!progressed) {
+        if (all_done) {
+          bool empty = true;
+          for (int w = 0; w < workers; ++w) empty = empty && w2s[(size_t)w * servers + s].empty();
+          if (empty) break;
+        }
+        std::this_thread::yield();
+      }
+    }
+    (void)m;
+  };
+
+  std::vector<std::thread> th;
+  for (int s = 0; s < servers; ++s) th.emplace_back(server, s);
+  for (int w = 0; w < workers; ++w) th.emplace_back(worker, w);
+  for (auto& t : th) t.join();
+  return bad.load() ? -2 : 0;
+}
+
+}  // extern "C"

@@ -110,3 +110,37 @@ def mf_train(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, nu
     if rc != 0:
         raise ValueError("bad arguments for the native MF engine (ids out of range, k > 128, ...)")
     return ut, it, utouch.astype(bool), itouch.astype(bool), float(sse.value)
+
+
+PA_ALGOS = {"PA": 0, "PAI": 1, "PAII": 2}
+
+
+def pa_binary(row_ptr, cols, vals, labels, feature_count: int, algo: str = "PA", aggressiveness: float = 0.0,
+              workers: int = 4, servers: int = 4, pull_limit: int = 10000, range_partitioning: bool = False,
+              weights=None):
+    """Binary passive-aggressive training / prediction on the native host engine
+    (``fps_host_pa_binary``).  CSR examples; ``labels`` +1 / -1 / 0 (= predict only).  ``weights``: optional
+    initial model (float32 [feature_count], updated in place).  Returns ``(pred, weights, touched)``."""
+    rp = np.ascontiguousarray(np.asarray(row_ptr, dtype=np.int64))
+    c = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
+    v = np.ascontiguousarray(np.asarray(vals, dtype=np.float32))
+    y = np.ascontiguousarray(np.asarray(labels, dtype=np.int32))
+    n = int(y.shape[0])
+    if weights is None:
+        weights = np.zeros(int(feature_count), dtype=np.float32)
+    if weights.dtype != np.float32 or not weights.flags["C_CONTIGUOUS"] or weights.shape[0] != feature_count:
+        raise ValueError("weights must be a contiguous float32 array of length feature_count")
+    pred = np.zeros(n, dtype=np.int32)
+    touched = np.zeros(int(feature_count), dtype=np.uint8)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib().fps_host_pa_binary(ptr(rp), ptr(c), ptr(v), ptr(y), C.c_int64(n), C.c_int64(feature_count),
+                                  C.c_int32(PA_ALGOS[algo]), C.c_float(aggressiveness), C.c_int32(workers),
+                                  C.c_int32(servers), C.c_int32(pull_limit), C.c_int32(1 if range_partitioning else 0),
+                                  ptr(weights), ptr(pred), ptr(touched))
+    if rc == -2:
+        from ..errors import FactorIsNotANumberException
+
+        raise FactorIsNotANumberException("non-finite passive-aggressive update in the native host engine")
+    if rc != 0:
+        raise ValueError("bad arguments for the native PA engine (feature id out of range, ...)")
+    return pred, weights, touched.astype(bool)

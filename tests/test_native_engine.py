@@ -108,3 +108,57 @@ def test_native_engine_is_race_free_under_thread_sanitizer(tmp_path):
     r = subprocess.run(["bash", os.path.join(repo, "scripts", "tsan_host.sh")], cwd=repo, capture_output=True,
                        text=True, timeout=900, env={**os.environ, "TMPDIR": str(tmp_path)})
     assert r.returncode == 0 and "tsan: clean" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _sparse(rnd, feats, nnz):
+    from fps_b200.models.pa.sparse import SparseVector
+
+    idx = rnd.sample(range(feats), nnz)
+    return SparseVector(idx, [rnd.gauss(0, 1) for _ in idx], feats)
+
+
+@pytest.mark.parametrize("algo_name,C", [("PA", 0.0), ("PAI", 0.05), ("PAII", 0.5)])
+@pytest.mark.parametrize("range_part", [False, True])
+def test_native_pa_sequential_equals_host_algorithm(algo_name, C, range_part):
+    """1 worker => examples are processed one after the other => must equal the host algorithm step by step
+    (any number of server threads: per-worker FIFO rings order pushes before later pulls)."""
+    from fps_b200.api import Left
+    from fps_b200.models.pa.algorithms import PassiveAggressiveBinaryAlgorithm as B
+    from fps_b200.models.pa.ps import transformBinary
+
+    rnd = random.Random(1)
+    feats = 3000
+    algo = {"PA": B.buildPA(), "PAI": B.buildPAI(C), "PAII": B.buildPAII(C)}[algo_name]
+    data, w = [], {}
+    for _ in range(80):
+        v, y = _sparse(rnd, feats, 40), rnd.random() < 0.5
+        data.append(Left((v, y)))
+        for i, d in algo.delta(v, {i: w.get(i, 0.0) for i in v.indices.tolist()}, y):
+            w[i] = w.get(i, 0.0) + d
+    out = transformBinary()(data, 1, 3, algo, 7, feats, range_part, 100, backend="native")
+    got = dict(out.ps_outputs())
+    assert {i for i, x in got.items() if x != 0} == {i for i, x in w.items() if x != 0}
+    for i, x in w.items():
+        assert abs(got[i] - x) < 1e-4 * max(1.0, abs(x))
+
+
+def test_native_pa_accuracy_gate_and_predict_with_model_load():
+    """PassiveAggressiveParameterServerTest.scala:44-100 on the native engine: accuracy >= 80 %."""
+    from fps_b200.api import Left, Right
+    from fps_b200.models.pa.algorithms import PassiveAggressiveBinaryAlgorithm as B
+    from fps_b200.models.pa.ps import transformBinary
+
+    rnd = random.Random(7)
+    feats = 50_000
+    w_true, data = {}, []
+    for _ in range(80):
+        v = _sparse(rnd, feats, 500)
+        s = sum(x * w_true.setdefault(i, rnd.gauss(0, 1)) for i, x in v.activeIterator())
+        data.append((v, s > 0))
+    out = transformBinary()([Left(d) for d in data] * 3, 3, 3, B.buildPA(), 100, feats, True, 100, backend="native")
+    model = dict(out.ps_outputs())
+    assert sum((v.dot(model) > 0) == y for v, y in data[:20]) / 20 >= 0.8
+    pred = transformBinary(list(model.items()))([Right((i, v)) for i, (v, _) in enumerate(data[:20])], 3, 3,
+                                                B.buildPA(), 100, feats, True, 100, backend="native")
+    got = pred.worker_outputs()
+    assert len(got) == 20 and sum(bool(p) == y for (_v, p), (_v2, y) in zip(got, data[:20])) / 20 >= 0.8
