@@ -149,6 +149,38 @@ def _transform_binary_native(model, inputSource, workerParallelism, psParallelis
     return ResultStream(out)
 
 
+def _transform_multiclass_native(model, inputSource, workerParallelism, psParallelism, algo, pullLimit, labelCount,
+                                 featureCount, rangePartitioning):
+    """``backend="native"`` of :func:`transformMulticlass` (``fps_host_pa_multiclass``)."""
+    import numpy as np
+
+    from ...ops import host
+    from ...runtime.stream import ResultStream, as_stream
+    from .device import algo_to_device
+
+    name, C, cost = algo_to_device(algo)
+    L = int(labelCount)
+    recs = as_stream(inputSource).collect()
+    weights = np.zeros((int(featureCount), L), dtype=np.float32)
+    if model is not None:
+        for fid, w in as_stream(model).collect():
+            weights[int(fid)] = np.asarray(w, dtype=np.float32)
+    row_ptr, cols, vals, labels = [0], [], [], []
+    for d in recs:
+        vec = d.value[0] if d.is_left else d.value[1]
+        cols.extend(vec.indices.tolist()); vals.extend(vec.values.tolist())
+        row_ptr.append(len(cols))
+        labels.append(int(d.value[1]) if d.is_left else -1)
+    pred, weights, touched = host.pa_multiclass(row_ptr, cols, vals, labels, int(featureCount), L, name, C, cost,
+                                                workers=workerParallelism, servers=psParallelism,
+                                                pull_limit=max(1, int(pullLimit)),
+                                                range_partitioning=bool(rangePartitioning), weights=weights)
+    out = [Left((d.value[1], int(p))) for d, p in zip(recs, pred) if not d.is_left]
+    keep = touched | (weights != 0).any(axis=1)
+    out += [Right((int(f), weights[f].astype("float64"))) for f in np.nonzero(keep)[0]]
+    return ResultStream(out)
+
+
 def transformBinary(model=None):
     """``transformBinary(model)(inputSource, workerParallelism, psParallelism, algo, pullLimit,
     featureCount, rangePartitioning, iterationWaitTime)``; input records are
@@ -178,6 +210,10 @@ def transformMulticlass(model=None):
     def run(inputSource, workerParallelism, psParallelism, passiveAggressiveMethod, pullLimit,
             labelCount, featureCount, rangePartitioning=False, iterationWaitTime=10000,
             backend="local", **kw):
+        if backend == "native":
+            return _transform_multiclass_native(model, inputSource, workerParallelism, psParallelism,
+                                                passiveAggressiveMethod, pullLimit, labelCount, featureCount,
+                                                rangePartitioning)
         if backend == "device":
             from .device import transform_multiclass_device
 

@@ -471,3 +471,165 @@ int fps_host_pa_binary(const int64_t* row_ptr, const int32_t* cols, const float*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Multiclass passive-aggressive on the native engine: one weight vector of `L` labels per feature;
+// one-versus-all PA / PA-I / PA-II (PassiveAggressiveOneVersusAll.scala:38-123) and the cost-based PB / ML
+// rules (PassiveAggressiveCostBased.scala:30-140).  Same protocol and rings as fps_host_pa_binary, with
+// L-vector payloads (L <= MF_MAX_K).
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+// labels[ex] in [0, L) or -1 (= predict only).  algo: 0 PA, 1 PA-I, 2 PA-II (one versus all), 3 PB, 4 ML
+// (cost based; cost[L*L] row = true label, may be null = 0/1 cost).  weights [feature_count, L] in/out.
+int fps_host_pa_multiclass(const int64_t* row_ptr, const int32_t* cols, const float* vals, const int32_t* labels,
+                           int64_t n, int64_t feature_count, int32_t L, int32_t algo, float C, const float* cost,
+                           int32_t workers, int32_t servers, int32_t pull_limit, int32_t range_partition,
+                           float* weights, int32_t* pred, uint8_t* touched) {
+  if (workers < 1 || servers < 1 || pull_limit < 1 || feature_count < 1 || algo < 0 || algo > 4 || L < 1 ||
+      L > MF_MAX_K)
+    return -1;
+  for (int64_t j = 0; j < row_ptr[n]; ++j)
+    if (cols[j] < 0 || cols[j] >= feature_count) return -1;
+  for (int64_t e = 0; e < n; ++e)
+    if (labels[e] < -1 || labels[e] >= L) return -1;
+  const int64_t div = (feature_count + servers - 1) / servers;
+  auto owner = [&](int32_t f) -> int {
+    if (!range_partition) return f % servers;
+    const int64_t s = f / div;
+    return (int)(s < servers ? s : servers - 1);
+  };
+  std::vector<MfRing> w2s((size_t)workers * servers), s2w((size_t)workers * servers);
+  for (auto& r : w2s) r.init(2 * (size_t)pull_limit + 64);
+  for (auto& r : s2w) r.init((size_t)pull_limit + 8);
+  std::atomic<int> workers_done{0};
+  std::atomic<int> bad{0};
+
+  auto worker = [&](int w) {
+    std::vector<std::vector<int64_t>> pend(servers);
+    std::vector<size_t> pend_head(servers, 0);
+    std::vector<float> dec(L), mult(L);
+    for (int64_t ex = w; ex < n; ex += workers) {
+      const int64_t b = row_ptr[ex], m = row_ptr[ex + 1] - b;
+      std::fill(dec.begin(), dec.end(), 0.f);
+      for (int s = 0; s < servers; ++s) { pend[s].clear(); pend_head[s] = 0; }
+      int64_t issued = 0, received = 0;
+      while (received < m) {
+        bool progressed = false;
+        while (issued < m && issued - received < pull_limit) {
+          const int s = owner(cols[b + issued]);
+          MfMsg* p = w2s[(size_t)w * servers + s].begin_push();
+          if (p == nullptr) break;
+          p->kind = 0; p->id = cols[b + issued];
+          w2s[(size_t)w * servers + s].end_push();
+          pend[s].push_back(issued);
+          ++issued; progressed = true;
+        }
+        for (int s = 0; s < servers; ++s) {
+          MfRing& in = s2w[(size_t)w * servers + s];
+          while (MfMsg* a = in.front()) {
+            const float x = vals[b + pend[s][pend_head[s]++]];
+            for (int l = 0; l < L; ++l) dec[l] += x * a->v[l];  // d = W^T x
+            in.pop();
+            ++received; progressed = true;
+          }
+        }
+        if (!progressed) std::this_thread::yield();
+      }
+      float nsq = 0.f;
+      for (int64_t j = 0; j < m; ++j) nsq += vals[b + j] * vals[b + j];
+      int arg = 0;
+      for (int l = 1; l < L; ++l)
+        if (dec[l] > dec[arg]) arg = l;
+      pred[ex] = arg;
+      const int y = labels[ex];
+      if (y < 0 || m == 0 || !(nsq > 0.f)) continue;
+      bool any = false;
+      if (algo <= 2) {
+        for (int l = 0; l < L; ++l) {
+          const float yl = l == y ? 1.f : -1.f;
+          const float loss = std::max(0.f, 1.f - yl * dec[l]);
+          float tau;
+          if (algo == 0) tau = loss / nsq;
+          else if (algo == 1) tau = std::min(C, loss / nsq);
+          else tau = loss / (nsq + 1.f / (2.f * C));
+          mult[l] = tau * yl;
+          any = any || mult[l] != 0.f;
+        }
+      } else {
+        int q = arg;  // PB: the predicted label; ML: the label maximising score difference + sqrt(cost)
+        if (algo == 4) {
+          float bestv = -3.0e38f;
+          for (int l = 0; l < L; ++l) {
+            const float c = cost ? cost[(size_t)y * L + l] : (l == y ? 0.f : 1.f);
+            const float v = dec[l] - dec[y] + std::sqrt(c);
+            if (v > bestv) { bestv = v; q = l; }
+          }
+        }
+        std::fill(mult.begin(), mult.end(), 0.f);
+        if (q != y) {
+          const float c = cost ? cost[(size_t)y * L + q] : 1.f;
+          const float tau = (dec[q] - dec[y] + std::sqrt(c)) / (2.f * nsq);
+          mult[y] = tau; mult[q] = -tau;
+          any = tau != 0.f;
+        }
+      }
+      if (!any) continue;
+      for (int64_t j = 0; j < m; ++j) {
+        const int s = owner(cols[b + j]);
+        MfRing& out = w2s[(size_t)w * servers + s];
+        MfMsg* p;
+        while ((p = out.begin_push()) == nullptr) std::this_thread::yield();
+        p->kind = 1; p->id = cols[b + j];
+        for (int l = 0; l < L; ++l) {
+          p->v[l] = vals[b + j] * mult[l];
+          if (!(std::fabs(p->v[l]) <= 3.0e38f)) bad = 1;
+        }
+        out.end_push();
+      }
+    }
+    workers_done.fetch_add(1, std::memory_order_release);
+  };
+
+  auto server = [&](int s) {
+    while (true) {
+      bool progressed = false;
+      const bool all_done = workers_done.load(std::memory_order_acquire) == workers;
+      for (int w = 0; w < workers; ++w) {
+        MfRing& in = w2s[(size_t)w * servers + s];
+        while (MfMsg* m = in.front()) {
+          float* row = weights + (int64_t)m->id * L;
+          if (m->kind == 0) {
+            MfRing& out = s2w[(size_t)w * servers + s];
+            MfMsg* a = out.begin_push();
+            if (a == nullptr) break;
+            a->kind = 2; a->id = m->id;
+            std::memcpy(a->v, row, sizeof(float) * L);
+            out.end_push();
+          } else {
+            for (int l = 0; l < L; ++l) row[l] += m->v[l];
+          }
+          touched[m->id] = 1;
+          in.pop();
+          progressed = true;
+        }
+      }
+      if (!progressed) {
+        if (all_done) {
+          bool empty = true;
+          for (int w = 0; w < workers; ++w) empty = empty && w2s[(size_t)w * servers + s].front() == nullptr;
+          if (empty) break;
+        }
+        std::this_thread::yield();
+      }
+    }
+  };
+
+  std::vector<std::thread> th;
+  for (int s = 0; s < servers; ++s) th.emplace_back(server, s);
+  for (int w = 0; w < workers; ++w) th.emplace_back(worker, w);
+  for (auto& t : th) t.join();
+  return bad.load() ? -2 : 0;
+}
+
+}  // extern "C"

@@ -144,3 +144,40 @@ def pa_binary(row_ptr, cols, vals, labels, feature_count: int, algo: str = "PA",
     if rc != 0:
         raise ValueError("bad arguments for the native PA engine (feature id out of range, ...)")
     return pred, weights, touched.astype(bool)
+
+
+PA_MULTI_ALGOS = {"PA": 0, "PAI": 1, "PAII": 2, "PB": 3, "ML": 4}
+
+
+def pa_multiclass(row_ptr, cols, vals, labels, feature_count: int, num_labels: int, algo: str = "PA",
+                  aggressiveness: float = 0.0, cost=None, workers: int = 4, servers: int = 4,
+                  pull_limit: int = 10000, range_partitioning: bool = False, weights=None):
+    """Multiclass passive-aggressive (one-versus-all PA / PAI / PAII, cost-based PB / ML) on the native host
+    engine (``fps_host_pa_multiclass``).  ``labels`` in ``[0, L)`` or -1 (= predict only); ``cost``: optional
+    ``[L, L]`` matrix (row = true label).  Returns ``(pred, weights [feature_count, L], touched)``."""
+    rp = np.ascontiguousarray(np.asarray(row_ptr, dtype=np.int64))
+    c = np.ascontiguousarray(np.asarray(cols, dtype=np.int32))
+    v = np.ascontiguousarray(np.asarray(vals, dtype=np.float32))
+    y = np.ascontiguousarray(np.asarray(labels, dtype=np.int32))
+    n, L = int(y.shape[0]), int(num_labels)
+    if weights is None:
+        weights = np.zeros((int(feature_count), L), dtype=np.float32)
+    if weights.dtype != np.float32 or not weights.flags["C_CONTIGUOUS"] or weights.shape != (feature_count, L):
+        raise ValueError("weights must be a contiguous float32 array [feature_count, num_labels]")
+    cm = None if cost is None else np.ascontiguousarray(np.asarray(cost, dtype=np.float32).reshape(L, L))
+    pred = np.zeros(n, dtype=np.int32)
+    touched = np.zeros(int(feature_count), dtype=np.uint8)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib().fps_host_pa_multiclass(ptr(rp), ptr(c), ptr(v), ptr(y), C.c_int64(n), C.c_int64(feature_count),
+                                      C.c_int32(L), C.c_int32(PA_MULTI_ALGOS[algo]), C.c_float(aggressiveness),
+                                      ptr(cm) if cm is not None else C.c_void_p(None), C.c_int32(workers),
+                                      C.c_int32(servers), C.c_int32(pull_limit),
+                                      C.c_int32(1 if range_partitioning else 0), ptr(weights), ptr(pred),
+                                      ptr(touched))
+    if rc == -2:
+        from ..errors import FactorIsNotANumberException
+
+        raise FactorIsNotANumberException("non-finite passive-aggressive update in the native host engine")
+    if rc != 0:
+        raise ValueError("bad arguments for the native PA engine (feature / label out of range, L > 128, ...)")
+    return pred, weights, touched.astype(bool)

@@ -7,6 +7,26 @@ extern "C" int fps_host_mf_train(const int32_t*, const int32_t*, const float*, i
                                  uint8_t*, uint8_t*, double*);
 extern "C" int fps_host_pa_binary(const int64_t*, const int32_t*, const float*, const int32_t*, int64_t, int64_t,
                                   int32_t, float, int32_t, int32_t, int32_t, int32_t, float*, int32_t*, uint8_t*);
+extern "C" int fps_host_pa_multiclass(const int64_t*, const int32_t*, const float*, const int32_t*, int64_t, int64_t,
+                                      int32_t, int32_t, float, const float*, int32_t, int32_t, int32_t, int32_t,
+                                      float*, int32_t*, uint8_t*);
+static void pa_multi_trials(std::mt19937& g) {
+  for (int trial = 0; trial < 6; ++trial) {
+    int W = 1 + g() % 5, S = 1 + g() % 5, L = 2 + g() % 9, lim = 1 + g() % 40;
+    int64_t feats = 200 + g() % 2000, n = 200 + g() % 1200;
+    std::vector<int64_t> rp(1, 0); std::vector<int32_t> cols; std::vector<float> vals; std::vector<int32_t> lab(n);
+    for (int64_t e = 0; e < n; ++e) {
+      int nnz = 1 + g() % 40;
+      for (int j = 0; j < nnz; ++j) { cols.push_back(g() % feats); vals.push_back((int)(g() % 2001 - 1000) / 1000.f); }
+      rp.push_back((int64_t)cols.size());
+      lab[e] = (int)(g() % (L + 1)) - 1;
+    }
+    std::vector<float> w((size_t)feats * L, 0.f); std::vector<int32_t> pred(n); std::vector<uint8_t> t(feats);
+    int rc = fps_host_pa_multiclass(rp.data(), cols.data(), vals.data(), lab.data(), n, feats, L, trial % 5, 0.1f,
+                                    nullptr, W, S, lim, trial & 1, w.data(), pred.data(), t.data());
+    std::printf("pa-multi trial %d W=%d S=%d L=%d n=%lld rc=%d\n", trial, W, S, L, (long long)n, rc);
+  }
+}
 static void pa_trials(std::mt19937& g) {
   for (int trial = 0; trial < 8; ++trial) {
     int W = 1 + g() % 5, S = 1 + g() % 5, L = 1 + g() % 40; int64_t feats = 200 + g() % 3000, n = 200 + g() % 1500;
@@ -36,5 +56,6 @@ int main() {
     std::printf("trial %d W=%d S=%d L=%d k=%d n=%lld rc=%d sse=%.3f\n", trial, W, S, L, k, (long long)n, rc, sse);
   }
   pa_trials(g);
+  pa_multi_trials(g);
   return 0;
 }

@@ -162,3 +162,33 @@ def test_native_pa_accuracy_gate_and_predict_with_model_load():
                                                 B.buildPA(), 100, feats, True, 100, backend="native")
     got = pred.worker_outputs()
     assert len(got) == 20 and sum(bool(p) == y for (_v, p), (_v2, y) in zip(got, data[:20])) / 20 >= 0.8
+
+
+@pytest.mark.parametrize("which", ["OVA_PA", "OVA_PAI", "OVA_PAII", "PB", "ML"])
+def test_native_multiclass_pa_sequential_equals_host_algorithm(which):
+    from fps_b200.api import Left, Right
+    from fps_b200.models.pa.algorithms import PassiveAggressiveCostBased as CB
+    from fps_b200.models.pa.algorithms import PassiveAggressiveOneVersusAll as OVA
+    from fps_b200.models.pa.ps import transformMulticlass
+
+    rnd = random.Random(2)
+    feats, L = 500, 5
+    cost = lambda a, b: 0.0 if a == b else 1.0 + 0.25 * abs(a - b)      # noqa: E731
+    algo = {"OVA_PA": OVA.buildPA(L), "OVA_PAI": OVA.buildPAI(L, 0.1), "OVA_PAII": OVA.buildPAII(L, 0.5),
+            "PB": CB.buildPB(cost, L), "ML": CB.buildML(cost, L)}[which]
+    data, w, host_pred = [], {}, []
+    for step in range(60):
+        v, y = _sparse(rnd, feats, 25), rnd.randrange(L)
+        model = {i: w.get(i, np.zeros(L)) for i in v.indices.tolist()}
+        if step % 4 == 3:                                   # every 4th record is a query
+            data.append(Right((step, v)))
+            host_pred.append(algo.predict(v, model))
+            continue
+        data.append(Left((v, y)))
+        for i, d in algo.delta(v, model, y):
+            w[i] = w.get(i, np.zeros(L)) + d
+    out = transformMulticlass()(data, 1, 3, algo, 7, L, feats, False, 100, backend="native")
+    assert [p for (_v, p) in out.worker_outputs()] == host_pred
+    got = dict(out.ps_outputs())
+    for i, x in w.items():
+        np.testing.assert_allclose(got[i], x, rtol=1e-4, atol=1e-5)
