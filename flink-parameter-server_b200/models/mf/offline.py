@@ -94,7 +94,8 @@ def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: fl
         from .native_api import ps_mf_native
 
         return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
-                            psParallelism, seed or 0, plain_residual, epochs=iterations)
+                            psParallelism, seed or 0, plain_residual, epochs=iterations,
+                            negativeSampleRate=negativeSampleRate, userMemory=userMemory)
     if backend == "device":
         from .device_api import ps_offline_mf_device
 

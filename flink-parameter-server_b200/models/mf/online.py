@@ -115,7 +115,8 @@ def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: flo
         from .native_api import ps_mf_native
 
         return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
-                            psParallelism, seed or 0, plain_residual, epochs=1)
+                            psParallelism, seed or 0, plain_residual, epochs=1,
+                            negativeSampleRate=negativeSampleRate, userMemory=userMemory)
     if backend == "device":
         from .device_api import ps_online_mf_device
 

@@ -187,8 +187,10 @@ int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* r
                       int32_t workers, int32_t servers, int32_t k, float lr, int32_t err_mode, float lo,
                       float hi, uint64_t seed, int32_t epochs, int32_t pull_limit, float* user_table,
                       int64_t num_users, float* item_table, int64_t num_items, uint8_t* user_touched,
-                      uint8_t* item_touched, double* sum_sq_err) {
-  if (workers < 1 || servers < 1 || k < 1 || k > MF_MAX_K || pull_limit < 1 || epochs < 1) return -1;
+                      uint8_t* item_touched, double* sum_sq_err, int32_t neg_rate, int32_t user_memory) {
+  if (workers < 1 || servers < 1 || k < 1 || k > MF_MAX_K || pull_limit < 1 || epochs < 1 || neg_rate < 0 ||
+      user_memory < 0)
+    return -1;
   for (int64_t i = 0; i < n; ++i)
     if (users[i] < 0 || users[i] >= num_users || items[i] < 0 || items[i] >= num_items) return -1;
   for (int64_t u = 0; u < num_users; ++u)
@@ -204,27 +206,58 @@ int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* r
   std::atomic<int> bad{0};
   std::vector<double> sq(workers, 0.0);
 
+  struct Rec { int32_t user, item; float rating; };
   auto worker = [&](int w) {
     std::vector<int64_t> mine;
     for (int64_t i = 0; i < n; ++i)
       if (users[i] % workers == w) mine.push_back(i);
-    std::vector<std::vector<int64_t>> pend(servers);  // FIFO of rating indices awaiting an answer, per server
+    std::vector<std::vector<Rec>> pend(servers);  // FIFO of records awaiting an answer, per server
     std::vector<size_t> pend_head(servers, 0);
+    // negative sampling state (PSOnlineMatrixFactorizationWorker.scala:61-78): the items this worker has
+    // seen so far, and per user the last `user_memory` rated items
+    std::vector<int32_t> item_ids;
+    std::vector<uint8_t> item_known(neg_rate > 0 ? (size_t)num_items : 0, 0);
+    std::unordered_map<int32_t, std::vector<int32_t>> seen_q;  // ring, oldest first
+    uint64_t rng = splitmix64(seed ^ (0xA5A5A5A5ull + (uint64_t)w));
+    std::vector<Rec> todo;  // records to issue for the current positive rating (negatives first)
+    size_t todo_pos = 0;
     double acc = 0.0;
     for (int ep = 0; ep < epochs; ++ep) {
       size_t next = 0;
       int outstanding = 0;
-      while (next < mine.size() || outstanding > 0) {
+      while (next < mine.size() || todo_pos < todo.size() || outstanding > 0) {
         bool progressed = false;
-        while (next < mine.size() && outstanding < pull_limit) {  // the pull limiter
-          const int64_t idx = mine[next];
-          const int s = items[idx] % servers;
+        while (outstanding < pull_limit) {  // the pull limiter
+          if (todo_pos == todo.size()) {
+            if (next == mine.size()) break;
+            const int64_t idx = mine[next++];
+            todo.clear(); todo_pos = 0;
+            if (neg_rate > 0) {
+              std::vector<int32_t>& q = seen_q[users[idx]];
+              if ((int)q.size() >= user_memory && !q.empty()) q.erase(q.begin());
+              if (user_memory > 0) q.push_back(items[idx]);
+              const int64_t room = (int64_t)item_ids.size() - (int64_t)q.size();
+              const int64_t k_neg = std::max<int64_t>(0, std::min<int64_t>(room, neg_rate));
+              for (int64_t t = 0; t < k_neg; ++t) {
+                int32_t cand;
+                do {
+                  rng = splitmix64(rng);
+                  cand = item_ids[(size_t)(rng % item_ids.size())];
+                } while (std::find(q.begin(), q.end(), cand) != q.end());
+                todo.push_back(Rec{users[idx], cand, 0.f});
+              }
+              if (!item_known[items[idx]]) { item_known[items[idx]] = 1; item_ids.push_back(items[idx]); }
+            }
+            todo.push_back(Rec{users[idx], items[idx], ratings[idx]});
+          }
+          const Rec& r = todo[todo_pos];
+          const int s = r.item % servers;
           MfMsg* m = w2s[(size_t)w * servers + s].begin_push();
           if (m == nullptr) break;
-          m->kind = 0; m->id = items[idx];
+          m->kind = 0; m->id = r.item;
           w2s[(size_t)w * servers + s].end_push();
-          pend[s].push_back(idx);
-          ++next; ++outstanding; progressed = true;
+          pend[s].push_back(r);
+          ++todo_pos; ++outstanding; progressed = true;
         }
         for (int s = 0; s < servers; ++s) {
           MfRing& in = s2w[(size_t)w * servers + s];
@@ -232,11 +265,11 @@ int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* r
             MfRing& out = w2s[(size_t)w * servers + s];
             MfMsg* p = out.begin_push();
             if (p == nullptr) break;  // cannot happen by the capacity argument; stay safe
-            const int64_t idx = pend[s][pend_head[s]++];
-            float* u = user_table + (int64_t)users[idx] * k;
+            const Rec r = pend[s][pend_head[s]++];
+            float* u = user_table + (int64_t)r.user * k;
             float dot = 0.f;
             for (int j = 0; j < k; ++j) dot += u[j] * a->v[j];
-            const float resid = ratings[idx] - dot;
+            const float resid = r.rating - dot;
             const float e = err_mode == 0 ? 1.f / (1.f + std::exp(-resid)) : resid;
             const float g = lr * e;
             if (!(std::fabs(g) <= 3.0e38f)) bad = 1;
@@ -248,7 +281,7 @@ int fps_host_mf_train(const int32_t* users, const int32_t* items, const float* r
             }
             out.end_push();
             in.pop();
-            user_touched[users[idx]] = 1;
+            user_touched[r.user] = 1;
             --outstanding; progressed = true;
           }
         }

@@ -81,7 +81,8 @@ class NativeInterner:
 def mf_train(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, num_users: int, num_items: int,
              num_factors: int = 10, range_min: float = -0.01, range_max: float = 0.01,
              learning_rate: float = 0.01, workers: int = 4, servers: int = 4, pull_limit: int = 1600,
-             epochs: int = 1, seed: int = 0, plain_residual: bool = False):
+             epochs: int = 1, seed: int = 0, plain_residual: bool = False, negative_sample_rate: int = 0,
+             user_memory: int = 128):
     """Asynchronous SGD matrix factorisation on the native host engine (``fps_host_mf_train``): worker and
     server *threads* exchanging pull / answer / push messages over lock-free SPSC rings with a pull limiter
     -- the reference's protocol at native speed, no GPU.  Returns ``(user_table, item_table, user_touched,
@@ -102,7 +103,7 @@ def mf_train(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, nu
         C.c_uint64(seed & (2**64 - 1)), C.c_int32(epochs), C.c_int32(pull_limit),
         ut.ctypes.data_as(C.c_void_p), C.c_int64(num_users), it.ctypes.data_as(C.c_void_p),
         C.c_int64(num_items), utouch.ctypes.data_as(C.c_void_p), itouch.ctypes.data_as(C.c_void_p),
-        C.byref(sse))
+        C.byref(sse), C.c_int32(negative_sample_rate), C.c_int32(user_memory))
     if rc == -2:
         from ..errors import FactorIsNotANumberException
 

@@ -4,7 +4,7 @@
 #include <random>
 extern "C" int fps_host_mf_train(const int32_t*, const int32_t*, const float*, int64_t, int32_t, int32_t, int32_t, float,
                                  int32_t, float, float, uint64_t, int32_t, int32_t, float*, int64_t, float*, int64_t,
-                                 uint8_t*, uint8_t*, double*);
+                                 uint8_t*, uint8_t*, double*, int32_t, int32_t);
 extern "C" int fps_host_pa_binary(const int64_t*, const int32_t*, const float*, const int32_t*, int64_t, int64_t,
                                   int32_t, float, int32_t, int32_t, int32_t, int32_t, float*, int32_t*, uint8_t*);
 extern "C" int fps_host_pa_multiclass(const int64_t*, const int32_t*, const float*, const int32_t*, int64_t, int64_t,
@@ -52,7 +52,7 @@ int main() {
     for (int64_t i = 0; i < n; ++i) { u[i] = g() % nu; it[i] = g() % ni; r[i] = (g() % 1000) / 1000.f; }
     std::vector<float> ut((size_t)nu * k), vt((size_t)ni * k); std::vector<uint8_t> a(nu), b(ni); double sse = 0;
     int rc = fps_host_mf_train(u.data(), it.data(), r.data(), n, W, S, k, 0.05f, trial & 1, -0.1f, 0.1f, 7, 1 + trial % 3, L,
-                               ut.data(), nu, vt.data(), ni, a.data(), b.data(), &sse);
+                               ut.data(), nu, vt.data(), ni, a.data(), b.data(), &sse, trial % 4, 1 + trial % 7);
     std::printf("trial %d W=%d S=%d L=%d k=%d n=%lld rc=%d sse=%.3f\n", trial, W, S, L, k, (long long)n, rc, sse);
   }
   pa_trials(g);

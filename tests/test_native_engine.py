@@ -192,3 +192,52 @@ def test_native_multiclass_pa_sequential_equals_host_algorithm(which):
     got = dict(out.ps_outputs())
     for i, x in w.items():
         np.testing.assert_allclose(got[i], x, rtol=1e-4, atol=1e-5)
+
+
+def test_native_mf_negative_sampling_matches_a_python_replica():
+    """Sequential mode again, now with negativeSampleRate / userMemory: the sampler (items seen so far by the
+    worker minus the user's recent items, splitmix64 stream) is replicated in Python, so tables must agree."""
+    rnd = random.Random(3)
+    nu, ni, k, n, neg, mem, seed = 15, 12, 5, 150, 2, 3, 9
+    u = [rnd.randrange(nu) for _ in range(n)]
+    i = [rnd.randrange(ni) for _ in range(n)]
+    r = [1.0] * n
+    ut, it, utc, itc, sse = host.mf_train(torch.tensor(u), torch.tensor(i), torch.tensor(r), nu, ni, k, -0.1, 0.1,
+                                         0.05, workers=1, servers=1, pull_limit=1, epochs=1, seed=seed,
+                                         plain_residual=True, negative_sample_rate=neg, user_memory=mem)
+    U = np.array([[_init(seed * 2 + 2, a, j, -0.1, 0.1) for j in range(k)] for a in range(nu)], dtype=np.float32)
+    V = np.array([[_init(seed * 2 + 1, a, j, -0.1, 0.1) for j in range(k)] for a in range(ni)], dtype=np.float32)
+    rng = _splitmix64(seed ^ (0xA5A5A5A5 + 0))
+    item_ids, known, seen = [], set(), {}
+    n_updates = 0
+
+    def update(a, b, c):
+        nonlocal n_updates
+        v = V[b].copy()
+        dot = np.float32(0)
+        for j in range(k):
+            dot = np.float32(dot + U[a, j] * v[j])
+        g = np.float32(np.float32(0.05) * np.float32(np.float32(c) - dot))
+        delta = (g * U[a]).astype(np.float32)
+        U[a] = (U[a] + g * v).astype(np.float32)
+        V[b] = (V[b] + delta).astype(np.float32)
+        n_updates += 1
+
+    for a, b, c in zip(u, i, r):
+        q = seen.setdefault(a, [])
+        if len(q) >= mem and q:
+            q.pop(0)
+        q.append(b)
+        for _ in range(max(0, min(len(item_ids) - len(q), neg))):
+            while True:
+                rng = _splitmix64(rng)
+                cand = item_ids[rng % len(item_ids)]
+                if cand not in q:
+                    break
+            update(a, cand, 0.0)
+        if b not in known:
+            known.add(b); item_ids.append(b)
+        update(a, b, c)
+    assert n_updates > n * 2                     # negatives were actually drawn
+    np.testing.assert_allclose(ut, U, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(it, V, rtol=2e-6, atol=1e-7)
