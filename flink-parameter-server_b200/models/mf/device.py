@@ -44,7 +44,8 @@ class DeviceOnlineMF:
                  kernel: Optional[str] = None, item_cache: Optional[bool] = None,
                  sync_every: int = 4, user_memory: int = 0,
                  sync_interval_ms: Optional[float] = None, item_blocking: Optional[bool] = None,
-                 block_bytes: int = 16 << 20):
+                 block_bytes: int = 16 << 20, flush_count: Optional[int] = None,
+                 flush_require: str = "any"):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -81,17 +82,21 @@ class DeviceOnlineMF:
                                        device=self.cuda_device)
                 self.seen_pos = torch.zeros(n_local, dtype=torch.int32, device=self.cuda_device)
         # ---- item-cache mode (sender-side combining) --------------------------------------------
-        # The worker trains a local replica of the item table (pulls and pushes stay in local HBM);
-        # every `sync_every` micro-batches a background stream pushes (replica - base) to the master
-        # shards and applies the other workers' contributions (master - base) to the replica: a row
-        # crosses NVLink once per exchange instead of once per update, overlapped with training.
-        # Still asynchronous (no barriers); staleness is bounded by ~2 x `sync_every` micro-batches.
+        # The worker trains a local owner-major replica of the item table (pulls and pushes stay in local
+        # HBM); its segments are the per-destination send buffers of the reference's batching senders.
+        # After every micro-batch a device-side count / timer policy (fps_flush_policy) picks the
+        # destinations to flush -- by default each destination once per `sync_every` micro-batches,
+        # staggered -- and a few TMA-driven CTAs (fps_replica_exchange) push (replica - base) to those
+        # master shards and fold the other workers' contributions (master - base) into the replica while
+        # the training kernel keeps running.  Asynchronous (no barriers); staleness ~ `sync_every` steps.
         if item_cache is None:
             item_cache = self.world > 1 and os.environ.get("FPS_ITEM_CACHE", "1") != "0"
         self.item_cache = bool(item_cache)
         self.sync_every = max(1, int(sync_every))
         self.sync_interval_ms = sync_interval_ms
-        self.replica = (ReplicaCache(self.items, self.sync_every, sync_interval_ms)
+        self.flush_count, self.flush_require = flush_count, flush_require
+        self.replica = (ReplicaCache(self.items, self.sync_every, sync_interval_ms,
+                                     require=flush_require, flush_count=flush_count)
                         if self.item_cache else None)
         # ---- L2 blocking: deal each micro-batch into buckets of <= 16 MB of item rows (fps_bucket.cu) ----
         # only where the item rows are read from local HBM (single GPU, or the local replica)
@@ -105,9 +110,12 @@ class DeviceOnlineMF:
         self.l2_hints = self.item_blocking and os.environ.get("FPS_L2_HINTS", "0") == "1"
         per_bucket = max(1, int(block_bytes) // row_bytes)
         self.block_shift = max(0, per_bucket.bit_length() - 1)
-        while -(-self.num_items >> self.block_shift) > native.BUCKET_MAX:
+        # buckets are ranges of rows of the table the fused kernel reads: the item shard (N = 1) or the
+        # owner-major replica (row = owner * rows_per_shard + slot)
+        table_rows = self.items.rows_per_shard * self.world if self.item_cache else self.num_items
+        while -(-table_rows >> self.block_shift) > native.BUCKET_MAX:
             self.block_shift += 1
-        self.block_buckets = max(1, -(-self.num_items >> self.block_shift))
+        self.block_buckets = max(1, -(-table_rows >> self.block_shift))
         if self.item_blocking:
             with torch.cuda.device(self.device):
                 self._bucket_scratch = torch.zeros(2 * native.BUCKET_MAX, dtype=torch.int32,
@@ -115,14 +123,6 @@ class DeviceOnlineMF:
         self.items.barrier()
 
     # ------------------------------------------------------------------------------------
-    @property
-    def cache(self):
-        return self.replica.cache
-
-    @property
-    def base(self):
-        return self.replica.base
-
     def flush(self) -> None:
         """Item-cache mode: push every pending local delta to the master shards and wait for it."""
         if self.replica is not None:
@@ -140,17 +140,25 @@ class DeviceOnlineMF:
                                                       self.seen, self.seen_pos, self.world,
                                                       seed=self.seed, step=self.step_no)
             neg = 0
+        n_records = users.numel()
+        fed = False
         if self.item_blocking and self.block_buckets > 1:
-            users, items, ratings = native.bucket_by_item(users, items, ratings, self.block_shift,
-                                                          self.block_buckets, self._bucket_scratch)
+            hashed = self.item_cache and self.items.mode == native.PART_HASH
+            fed = hashed
+            users, items, ratings = native.bucket_by_item(
+                users, items, ratings, self.block_shift, self.block_buckets, self._bucket_scratch,
+                num_shards=self.world if hashed else 1, rows_per_shard=self.items.rows_per_shard,
+                pending=self.replica.pending if hashed else None)
         if self.item_cache:
+            # policy + exchange kernels of this micro-batch go first (side stream): their CTAs take the
+            # slots the training grid leaves free
+            self.replica.after_step(n_records * (1 + neg), fed=fed)
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.replica.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints,
-                                reserve_ctas=self.replica.reserve())
-            self.replica.after_step()
+                                reserve_total=self.replica.reserve_total())
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
@@ -263,7 +271,8 @@ class DeviceOnlineMF:
         self.step_no = int(d["step_no"])
         self.items.barrier()
         if self.replica is not None:
-            self.replica = ReplicaCache(self.items, self.sync_every, self.sync_interval_ms)
+            self.replica = ReplicaCache(self.items, self.sync_every, self.sync_interval_ms,
+                                        require=self.flush_require, flush_count=self.flush_count)
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:
@@ -272,6 +281,13 @@ class DeviceOnlineMF:
     def barrier(self) -> None:
         self.flush()
         self.items.barrier()
+
+    def refresh(self) -> None:
+        """Collective quiesce: every delta is in the masters and every replica equals the master."""
+        if self.replica is not None:
+            self.replica.refresh()
+        else:
+            self.items.barrier()
 
     def close(self) -> None:
         self.items.close()

@@ -49,13 +49,15 @@ class DeviceSkipGram:
             self._ones = torch.ones(centers.numel(), dtype=torch.float32, device=self.dev)
         tin = self.rep_in.table_c if self.rep_in else self.w_in.table_c
         tout = self.rep_out.table_c if self.rep_out else self.w_out.table_c
+        if self.rep_in:   # policy + exchange kernels first (side streams), then the training kernel
+            n = centers.numel() * (1 + self.negative)
+            self.rep_in.after_step(n); self.rep_out.after_step(n)
         native.mf_sgd_fused(centers, contexts, self._ones, tin, 1, tout, self.lr,
                             err_mode=ERR_LOGISTIC, neg_rate=self.negative, num_items=self.vocab,
                             seed=self.seed, step=self.step_no, stats=self.stats, nan_flag=self.nan_flag,
                             kernel="reg",
-                            reserve_ctas=(self.rep_in.reserve() + self.rep_out.reserve()) if self.rep_in else 0)
-        if self.rep_in:
-            self.rep_in.after_step(); self.rep_out.after_step()
+                            reserve_total=(self.rep_in.reserve_total() + self.rep_out.reserve_total())
+                            if self.rep_in else 0)
         self.step_no += 1
 
     def flush(self) -> None:

@@ -27,12 +27,16 @@ struct BucketArgs {
   long long n;
   int format;
   int id_bytes;        // 4 or 8 (format 0)
-  int shift;           // bucket = item >> shift
-  int n_buckets;
+  int shift;           // bucket = row >> shift, row = owner(item) * rps + slot(item): the row index of the
+  int n_buckets;       //   owner-major table the fused kernel reads (num_shards == 1: row == item)
   unsigned int* scratch;  // [2 * BK_MAX]: totals, cursors (zeroed by the launcher)
   void* out_users;
   void* out_items;
   float* out_ratings;
+  long long rps;       // rows per owner segment
+  int num_shards;      // owners (hash partition item % num_shards); 1 = plain item >> shift
+  int shard_shift;     // log2(num_shards) or -1
+  unsigned long long* pending;  // optional [num_shards]: += records per destination (device-side CountLogic feed)
 };
 
 __device__ __forceinline__ long long bk_item(const BucketArgs& a, long long i) {
@@ -41,21 +45,40 @@ __device__ __forceinline__ long long bk_item(const BucketArgs& a, long long i) {
   if (a.id_bytes == 8) return reinterpret_cast<const long long*>(a.items)[i];
   return (long long)reinterpret_cast<const int*>(a.items)[i];
 }
+__device__ __forceinline__ int bk_owner(const BucketArgs& a, long long item) {
+  if (a.num_shards <= 1) return 0;
+  const unsigned long long u = (unsigned long long)(item < 0 ? -item : item);
+  return a.shard_shift >= 0 ? (int)(u & (unsigned long long)(a.num_shards - 1)) : (int)(u % (unsigned)a.num_shards);
+}
 __device__ __forceinline__ int bk_bucket(const BucketArgs& a, long long item) {
-  long long b = (item < 0 ? 0 : item) >> a.shift;
+  long long row = item < 0 ? -item : item;
+  if (a.num_shards > 1) {
+    const unsigned long long u = (unsigned long long)row;
+    const unsigned long long slot = a.shard_shift >= 0 ? (u >> a.shard_shift) : (u / (unsigned)a.num_shards);
+    row = (long long)bk_owner(a, item) * a.rps + (long long)slot;
+  }
+  const long long b = row >> a.shift;
   return (int)(b < a.n_buckets ? b : a.n_buckets - 1);
 }
 
 __global__ void __launch_bounds__(BK_THREADS) fps_bucket_hist_kernel(const BucketArgs a) {
   __shared__ unsigned int hist[BK_MAX];
+  __shared__ unsigned int ohist[FPS_MAX_SHARDS];
   if (threadIdx.x < BK_MAX) hist[threadIdx.x] = 0;
+  if (threadIdx.x < FPS_MAX_SHARDS) ohist[threadIdx.x] = 0;
   __syncthreads();
+  const bool feed = a.pending != nullptr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n;
-       i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&hist[bk_bucket(a, bk_item(a, i))], 1u);
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long item = bk_item(a, i);
+    atomicAdd(&hist[bk_bucket(a, item)], 1u);
+    if (feed) atomicAdd(&ohist[bk_owner(a, item)], 1u);
+  }
   __syncthreads();
   if (threadIdx.x < a.n_buckets && hist[threadIdx.x] != 0)
     atomicAdd(a.scratch + threadIdx.x, hist[threadIdx.x]);
+  if (feed && threadIdx.x < a.num_shards && ohist[threadIdx.x] != 0)
+    atomicAdd(a.pending + threadIdx.x, (unsigned long long)ohist[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(BK_THREADS) fps_bucket_scatter_kernel(const BucketArgs a) {

@@ -9,6 +9,7 @@
 // PSOnlineMatrixFactorizationWorker.scala:42-89 (worker step + negative sampling).
 #include <cuda_fp16.h>
 #include "fps_common.cuh"
+#include "fps_mf_args.cuh"
 
 // ----------------------------------------------------------------------------------------
 // K4: materialise rows as a pure function of (seed, id, column).
@@ -67,33 +68,6 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
 // The pull limiter (WL:196-250) is the number of row slots in flight: grid * 256 / LPR * R,
 // chosen by the host from pullLimit (credits pre-distributed to resident lane-groups).
 // ----------------------------------------------------------------------------------------
-struct MfArgs {
-  const void* users;
-  const void* items;
-  const float* ratings;
-  long long n_pos;
-  int neg_rate;
-  long long num_items;        // negative-sample id range [0, num_items)
-  unsigned long long seed;    // negative-sample stream key
-  unsigned long long step;    // negative-sample stream counter (micro-batch number)
-  float* user_table;          // worker-local [n_local_users, stride]
-  int user_div;               // workerParallelism: local slot = user / user_div
-  int user_shift;             // log2(user_div) if power of two, else -1
-  float lr;
-  int err_mode;               // 0: reference parity sigmoid(r - u.v); 1: plain residual r - u.v;
-                              // 2: logistic r - sigmoid(u.v) (skip-gram negative sampling)
-  int format;                 // 0: users/items/ratings arrays; 1: packed64 records in `users`
-                              //    (user:26 | item:22 | rating fp16:16) -- 8 B/update over PCIe
-  float* stats;               // [0] += sum (r-u.v)^2, [1] += #updates
-  int* nan_flag;              // set to 1 if a non-finite update was produced
-  ShardTable item_tab;
-  ShardTable user_tab;        // used when user_sharded != 0: the "user" rows also live on the PS
-  int user_sharded;           //   (word2vec: input vectors and output vectors are both PS tables)
-  int use_push_tab;           // != 0: item deltas are pushed into push_tab instead of item_tab
-  ShardTable push_tab;        //   (worker-side delta staging of the item-cache mode, see fps_cache_sync)
-  int l2_hints;               // != 0: item rows evict_last, user rows evict_first (L2-blocked batches)
-  int pad2_;
-};
 
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
 __global__ void __launch_bounds__(256, MINB)
@@ -116,6 +90,8 @@ __global__ void __launch_bounds__(256, MINB)
   bool bad = false;
 
   for (long long base = 0; base < n_eff; base += n_groups * R) {
+    if (a.progress != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+      *reinterpret_cast<volatile unsigned int*>(a.progress) = (unsigned int)base;
     float4 u[R][VPL], v[R][VPL];
     float* up[R];
     float* vp[R];
@@ -231,8 +207,10 @@ __global__ void __launch_bounds__(256, MINB)
   if (bad && a.nan_flag != nullptr) *a.nan_flag = 1;
 }
 
-static int g_mf_reserve = 0;  // CTA slots per SM left free for a concurrently running exchange kernel
+static int g_mf_reserve = 0;        // CTA slots per SM left free for a concurrently running kernel
+static int g_mf_reserve_total = 0;  // CTA slots left free on the whole GPU (the replica exchange CTAs)
 extern "C" void fps_set_mf_reserve(int v) { g_mf_reserve = v < 0 ? 0 : v; }
+extern "C" void fps_set_mf_reserve_total(int v) { g_mf_reserve_total = v < 0 ? 0 : v; }
 
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
@@ -243,7 +221,8 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
       &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT>, threads, 0);
   occ -= g_mf_reserve;  // leave slots for the background replica exchange (see fps_cache_sync)
   if (occ < 1) occ = 1;
-  long long blocks = (long long)num_sms * occ;
+  long long blocks = (long long)num_sms * occ - g_mf_reserve_total;
+  if (blocks < num_sms) blocks = num_sms;
   // pull limiter: rows in flight = blocks * groups_per_block * R  <=  pullLimit
   if (max_inflight_rows > 0) {
     long long cap = max_inflight_rows / ((long long)groups_per_block * R);
@@ -584,148 +563,3 @@ extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_byte
   return (int)cudaGetLastError();
 }
 
-// ----------------------------------------------------------------------------------------
-// Item-cache mode (sender-side combining -- the aggregated form of the reference's batching senders,
-// M/common/CombinationLogic.scala): a worker trains a LOCAL replica of the item table with the fused
-// kernel (pulls and pushes are local) while a background stream exchanges deltas with the masters:
-//   phase A (push_delta): d = replica - base; REDG d into the master row (owner's HBM over NVLink);
-//            base = the replica value just read.          [one transfer per row per sync, not per update]
-//   phase B (refresh):    f = master - base  (= what OTHER workers contributed since the last sync);
-//            replica += f (local REDG, so concurrent training updates are never lost); base = master.
-// Invariant: replica - base == local updates not yet pushed.  Both phases may run concurrently with
-// the training kernel; the kernel boundary between A and B makes the worker's own reductions visible
-// to its refresh.  Asynchronous (no barriers); staleness is bounded by the sync period.
-// ----------------------------------------------------------------------------------------
-template <int LPR>
-__global__ void __launch_bounds__(256)
-    fps_cache_push_delta_kernel(const __grid_constant__ ShardTable master,
-                                const float* __restrict__ cache, float* __restrict__ base,
-                                long long n_rows) {
-  const int lane = threadIdx.x & (LPR - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
-  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
-  const int stride = master.stride;
-  const int nvec = stride >> 2;
-  for (long long i = group; i < n_rows; i += n_groups) {
-    float* m = fps_row(master, i);
-    for (int q = lane; q < nvec; q += LPR) {
-      const float4 c = fps_ld_row4(cache + i * (long long)stride + 4 * q);
-      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
-      const float4 b = *bp;
-      const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
-      if (d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f) {
-        fps_red_add4(m + 4 * q, d);
-        *bp = c;
-      }
-    }
-  }
-}
-
-template <int LPR>
-__global__ void __launch_bounds__(256)
-    fps_cache_refresh_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
-                             float* __restrict__ base, long long n_rows) {
-  const int lane = threadIdx.x & (LPR - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
-  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
-  const int stride = master.stride;
-  const int nvec = stride >> 2;
-  for (long long i = group; i < n_rows; i += n_groups) {
-    const float* m = fps_row(master, i);
-    for (int q = lane; q < nvec; q += LPR) {
-      const float4 v = fps_ld_row4(m + 4 * q);
-      float4* bp = reinterpret_cast<float4*>(base + i * (long long)stride + 4 * q);
-      const float4 b = *bp;
-      const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
-      if (f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f) {
-        fps_red_add4(cache + i * (long long)stride + 4 * q, f);   // foreign contributions
-        *bp = v;
-      }
-    }
-  }
-}
-
-// Single-pass form of the two phases (default): with c = replica, b = base, v = master as read now,
-//   push   d = c - b  (REDG into the master row),      foreign  f = v - b  (REDG into the replica),
-//   base <- v + d     ("the master as this worker knows it, its own delta included").
-// Afterwards replica - base = (c + f + later local updates) - (v + d) = later local updates, the same
-// invariant as above, but every array is read once and base is written once: ~1.0 GB instead of ~1.8 GB
-// of local HBM traffic per exchange of a 256 MB table, and one launch instead of two.
-template <int LPR>
-__global__ void __launch_bounds__(256)
-    fps_cache_exchange_kernel(const __grid_constant__ ShardTable master, float* __restrict__ cache,
-                              float* __restrict__ base, long long n_rows) {
-  const int lane = threadIdx.x & (LPR - 1);
-  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
-  const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
-  const int stride = master.stride;
-  const int nvec = stride >> 2;
-  // two rows per step: all six loads (two of them possibly over NVLink) are issued before any use, so
-  // the kernel keeps its bandwidth when it is confined to one or two CTAs per SM next to training
-  for (long long i0 = group; i0 < n_rows; i0 += 2 * n_groups) {
-    const long long i1 = i0 + n_groups;
-    const bool two = i1 < n_rows;
-    float* m0 = fps_row(master, i0);
-    float* m1 = two ? fps_row(master, i1) : m0;
-    for (int q = lane; q < nvec; q += LPR) {
-      float* cp0 = cache + i0 * (long long)stride + 4 * q;
-      float* cp1 = cache + (two ? i1 : i0) * (long long)stride + 4 * q;
-      float4* bp0 = reinterpret_cast<float4*>(base + i0 * (long long)stride + 4 * q);
-      float4* bp1 = reinterpret_cast<float4*>(base + (two ? i1 : i0) * (long long)stride + 4 * q);
-      const float4 v0 = fps_ld_row4(m0 + 4 * q);   // owner's HBM (NVLink for remote shards)
-      const float4 v1 = fps_ld_row4(m1 + 4 * q);
-      const float4 c0 = fps_ld_row4(cp0);
-      const float4 c1 = fps_ld_row4(cp1);
-      const float4 b0 = *bp0;
-      const float4 b1 = *bp1;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (r == 1 && !two) break;
-        const float4 v = r ? v1 : v0, c = r ? c1 : c0, b = r ? b1 : b0;
-        float* m = (r ? m1 : m0) + 4 * q;
-        float* cp = r ? cp1 : cp0;
-        float4* bp = r ? bp1 : bp0;
-        const float4 d = make_float4(c.x - b.x, c.y - b.y, c.z - b.z, c.w - b.w);
-        const float4 f = make_float4(v.x - b.x, v.y - b.y, v.z - b.z, v.w - b.w);
-        const bool has_d = d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f;
-        const bool has_f = f.x != 0.f || f.y != 0.f || f.z != 0.f || f.w != 0.f;
-        if (has_d) fps_red_add4(m, d);     // my updates since the last exchange
-        if (has_f) fps_red_add4(cp, f);    // the other workers' updates since the last exchange
-        if (has_d || has_f) *bp = make_float4(v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w);
-      }
-    }
-  }
-}
-
-#define FPS_SYNC_DISPATCH(KERNEL, ...)                                         \
-  switch (lpr) {                                                               \
-    case 1: KERNEL<1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-    case 2: KERNEL<2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-    case 4: KERNEL<4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-    case 8: KERNEL<8><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;           \
-    case 16: KERNEL<16><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;         \
-    default: KERNEL<32><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;         \
-  }
-
-static int g_cache_sync_variant = 0;  // 0: single-pass exchange, 1: two-phase (push_delta, refresh)
-extern "C" void fps_set_cache_sync_variant(int v) { g_cache_sync_variant = v; }
-
-// ctas_per_sm > 0 confines the exchange to that many CTAs per SM (grid-stride over the rows) so that it
-// runs NEXT TO a training kernel that left the same number of slots free (fps_set_mf_reserve), instead
-// of queueing behind / in front of a kernel that fills every SM.
-extern "C" int fps_cache_sync(const ShardTable* master, float* cache, float* base, long long n_rows,
-                              int num_sms, int ctas_per_sm, cudaStream_t stream) {
-  if (n_rows <= 0) return 0;
-  const int lpr = pick_lpr(master->stride >> 2);
-  int grid = row_grid(n_rows, lpr, num_sms);
-  if (ctas_per_sm > 0 && grid > num_sms * ctas_per_sm) grid = num_sms * ctas_per_sm;
-  if (g_cache_sync_variant == 0) {
-    FPS_SYNC_DISPATCH(fps_cache_exchange_kernel, *master, cache, base, n_rows)
-    return (int)cudaGetLastError();
-  }
-  FPS_SYNC_DISPATCH(fps_cache_push_delta_kernel, *master, cache, base, n_rows)
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  FPS_SYNC_DISPATCH(fps_cache_refresh_kernel, *master, cache, base, n_rows)
-  return (int)cudaGetLastError();
-}

@@ -17,72 +17,14 @@
 // Reference behaviour reproduced: PSOnlineMatrixFactorizationWorker.scala:42-89, SGDUpdater.scala:8,
 // SimplePSLogic.scala:13-25 (see fps_core.cu for the semantics notes).
 #include "fps_common.cuh"
+#include "fps_mf_args.cuh"
+#include "fps_tma.cuh"
 
-struct MfArgs {  // must match fps_core.cu
-  const void* users;
-  const void* items;
-  const float* ratings;
-  long long n_pos;
-  int neg_rate;
-  long long num_items;
-  unsigned long long seed;
-  unsigned long long step;
-  float* user_table;
-  int user_div;
-  int user_shift;
-  float lr;
-  int err_mode;
-  int format;
-  float* stats;
-  int* nan_flag;
-  ShardTable item_tab;
-  ShardTable user_tab;
-  int user_sharded;
-  int use_push_tab;
-  ShardTable push_tab;
-};
 
 #define TILE_ROWS 32
 #define N_PRODUCER_WARPS 2
 #define N_CONSUMER_WARPS 8
 #define TMA_THREADS (32 * (N_PRODUCER_WARPS + N_CONSUMER_WARPS))
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA 1-D bulk copy global (local HBM or peer over NVLink) -> shared, completing on an mbarrier.
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 
 struct RowMeta {
   float* up;     // user row (worker-local HBM)
@@ -112,7 +54,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], N_CONSUMER_WARPS);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
 

@@ -68,6 +68,7 @@ class MfArgsC(C.Structure):
         ("push_tab", ShardTableC),
         ("l2_hints", C.c_int),
         ("pad2_", C.c_int),
+        ("progress", C.c_void_p),
     ]
 
 
@@ -230,7 +231,8 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  step: int = 0, stats: Optional[torch.Tensor] = None,
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
                  kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None,
-                 l2_hints: bool = False, reserve_ctas: int = 0) -> None:
+                 l2_hints: bool = False, reserve_ctas: int = 0, reserve_total: int = 0,
+                 progress: Optional[torch.Tensor] = None) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -274,7 +276,9 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
     if packed or push_tab is not None or l2_hints:
         variant = "reg"
+    a.progress = progress.data_ptr() if progress is not None else None
     lib().fps_set_mf_reserve(int(reserve_ctas))
+    lib().fps_set_mf_reserve_total(int(reserve_total))
     rv = os.environ.get("FPS_MF_REG_VARIANT")
     if rv is not None:
         lib().fps_set_mf_reg_variant(int(rv))
@@ -344,6 +348,8 @@ class BucketArgsC(C.Structure):
         ("format", C.c_int), ("id_bytes", C.c_int), ("shift", C.c_int), ("n_buckets", C.c_int),
         ("scratch", C.c_void_p), ("out_users", C.c_void_p), ("out_items", C.c_void_p),
         ("out_ratings", C.c_void_p),
+        ("rps", C.c_longlong), ("num_shards", C.c_int), ("shard_shift", C.c_int),
+        ("pending", C.c_void_p),
     ]
 
 
@@ -351,10 +357,15 @@ BUCKET_MAX = 64
 
 
 def bucket_by_item(users: torch.Tensor, items: Optional[torch.Tensor], ratings: Optional[torch.Tensor],
-                   shift: int, n_buckets: int, scratch: torch.Tensor):
-    """Reorder a micro-batch by ``item >> shift`` (L2 blocking of the item table, csrc/fps_bucket.cu).
+                   shift: int, n_buckets: int, scratch: torch.Tensor, num_shards: int = 1,
+                   rows_per_shard: int = 0, pending: Optional[torch.Tensor] = None):
+    """Reorder a micro-batch by ``row(item) >> shift`` (L2 blocking of the item table,
+    csrc/fps_bucket.cu); ``row`` is the row of the owner-major table the fused kernel reads
+    (``(item % num_shards) * rows_per_shard + item // num_shards``; plain ``item`` for one shard).
     ``items=None``: ``users`` holds packed64 records.  ``scratch``: int32 device tensor of
-    ``2 * BUCKET_MAX`` elements.  Returns the reordered ``(users, items, ratings)`` (new tensors)."""
+    ``2 * BUCKET_MAX`` elements.  ``pending``: optional int64 ``[num_shards]`` device counters that
+    receive the number of records per destination shard (feed of the device-side flush policy).
+    Returns the reordered ``(users, items, ratings)`` (new tensors)."""
     _req(users, "users"); _req(scratch, "scratch", torch.int32)
     packed = items is None
     a = BucketArgsC()
@@ -373,6 +384,11 @@ def bucket_by_item(users: torch.Tensor, items: Optional[torch.Tensor], ratings: 
         a.out_items = oi.data_ptr(); a.out_ratings = orat.data_ptr()
         a.format = 0; a.id_bytes = _id_bytes(users)
     a.shift = int(shift); a.n_buckets = int(n_buckets); a.scratch = scratch.data_ptr()
+    a.num_shards = max(1, int(num_shards)); a.shard_shift = log2_or_neg(a.num_shards)
+    a.rps = int(rows_per_shard)
+    if pending is not None:
+        _req(pending, "pending", torch.int64)
+        a.pending = pending.data_ptr()
     _check(lib().fps_bucket_by_item(C.byref(a), sm_count(users.device.index), _stream()), "bucket_by_item")
     _bump(2)
     return ou, oi, orat
@@ -434,20 +450,80 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
     return tc
 
 
-_CACHE_SYNC_TWO_PHASE = os.environ.get("FPS_CACHE_SYNC", "fused") == "2phase"
+class FlushPolicyC(C.Structure):
+    """Mirror of ``struct FlushPolicy`` (csrc/fps_replica.cu)."""
+
+    _fields_ = [("count_max", C.c_ulonglong), ("interval_ns", C.c_ulonglong),
+                ("add_uniform", C.c_ulonglong), ("require_all", C.c_int), ("force", C.c_int),
+                ("num_dest", C.c_int), ("pad_", C.c_int)]
 
 
-def cache_sync(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor, ctas_per_sm: int = 0) -> None:
-    """One delta exchange of a replica with its master shards: push ``replica - base``, fold the other
-    workers' ``master - base`` into the replica, ``base <- master + pushed delta`` (one streaming
-    kernel; ``FPS_CACHE_SYNC=2phase`` selects the original push_delta + refresh pair)."""
+FLUSH_STATE_WORDS = 3 * FPS_MAX_SHARDS + 1   # int64 words of ``struct FlushState``
+FLUSH_PENDING, FLUSH_LAST_NS, FLUSH_COUNT, FLUSH_MASK = 0, FPS_MAX_SHARDS, 2 * FPS_MAX_SHARDS, 3 * FPS_MAX_SHARDS
+
+
+def flush_policy(state: torch.Tensor, num_dest: int, count_max: int = 0, interval_ns: int = 0,
+                 require_all: bool = False, force: bool = False, add_uniform: int = 0) -> None:
+    """Device-side CountLogic / TimerLogic (CountLogic.scala:5-29, TimerLogic.scala:6-51) for the
+    per-destination send buffers of a replica: decides ON THE GPU which destinations to flush now
+    (messages buffered >= ``count_max`` and/or ``globaltimer`` deadline ``interval_ns`` passed, OR /
+    AND) and leaves the bit mask in ``state`` (int64 ``[FLUSH_STATE_WORDS]``) for the exchange kernel."""
+    _req(state, "state", torch.int64)
+    assert state.numel() >= FLUSH_STATE_WORDS
+    p = FlushPolicyC()
+    p.count_max = int(count_max); p.interval_ns = int(interval_ns); p.add_uniform = int(add_uniform)
+    p.require_all = int(bool(require_all)); p.force = int(bool(force)); p.num_dest = int(num_dest)
+    _check(lib().fps_flush_policy(C.byref(p), C.c_void_p(state.data_ptr()), _stream()), "flush_policy")
+    _bump()
+
+
+class ExchArgsC(C.Structure):
+    """Mirror of ``struct ExchArgs`` (csrc/fps_replica.cu)."""
+
+    _fields_ = [("master", ShardTableC), ("cache", C.c_void_p), ("base", C.c_void_p),
+                ("rps", C.c_longlong), ("slot_lo", C.c_longlong), ("slot_hi", C.c_longlong),
+                ("state", C.c_void_p), ("mask_override", C.c_uint), ("n_stages", C.c_int),
+                ("chunk_rows", C.c_int), ("sequential", C.c_int)]
+
+
+def replica_exchange(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor, *,
+                     state: Optional[torch.Tensor] = None, mask: int = 0, n_ctas: int = 32,
+                     n_stages: int = 4, slot_lo: int = 0, slot_hi: Optional[int] = None,
+                     sequential: bool = False) -> None:
+    """One delta exchange between an owner-major replica and its master shards for the destinations
+    flagged in ``state`` (written by :func:`flush_policy`) or in ``mask``: push ``replica - base``
+    (REDG over NVLink), fold ``master - base`` into the replica, ``base <- master + pushed delta``.
+    TMA bulk reads through a shared-memory ring; ``n_ctas`` CTAs.  csrc/fps_replica.cu."""
     _req(cache, "cache", torch.float32); _req(base, "base", torch.float32)
+    rps = int(master.rows_per_shard)
     assert cache.shape == base.shape and cache.shape[1] == master.stride
-    lib().fps_set_cache_sync_variant(1 if _CACHE_SYNC_TWO_PHASE else 0)
-    _check(lib().fps_cache_sync(C.byref(master), C.c_void_p(cache.data_ptr()),
-                                C.c_void_p(base.data_ptr()), C.c_longlong(cache.shape[0]),
-                                sm_count(cache.device.index), int(ctas_per_sm), _stream()), "cache_sync")
-    _bump(2 if _CACHE_SYNC_TWO_PHASE else 1)
+    assert cache.shape[0] == rps * master.num_shards
+    a = ExchArgsC()
+    a.master = master; a.cache = cache.data_ptr(); a.base = base.data_ptr(); a.rps = rps
+    a.slot_lo = int(slot_lo); a.slot_hi = rps if slot_hi is None else int(slot_hi)
+    if state is not None:
+        _req(state, "state", torch.int64)
+        a.state = state.data_ptr()
+    a.mask_override = int(mask) & 0xFFFFFFFF
+    a.n_stages = int(n_stages); a.sequential = int(bool(sequential))
+    _check(lib().fps_replica_exchange(C.byref(a), int(n_ctas), _stream()), "replica_exchange")
+    _bump()
+
+
+def segment_table(t: torch.Tensor, master: ShardTableC) -> ShardTableC:
+    """ShardTable over a LOCAL owner-major ``[num_shards * rps, stride]`` tensor: the same
+    ``id -> (owner, slot)`` map as ``master``, every "shard" in local HBM (a worker replica)."""
+    _req(t, "table", torch.float32)
+    n = int(master.num_shards)
+    rps = int(master.rows_per_shard)
+    assert t.shape[0] == n * rps and t.shape[1] == master.stride
+    tc = ShardTableC()
+    for o in range(n):
+        tc.base[o] = t.data_ptr() + o * rps * t.shape[1] * 4
+    tc.rows_per_shard = rps; tc.div = master.div; tc.num_shards = n
+    tc.dim = master.dim; tc.stride = master.stride; tc.mode = master.mode
+    tc.shard_shift = master.shard_shift
+    return tc
 
 
 def pull_dot(tab: ShardTableC, ids: torch.Tensor, local: torch.Tensor, score: torch.Tensor) -> None:

@@ -1,23 +1,30 @@
-"""Worker-side replica of a sharded table with background delta exchange (sender-side combining).
+"""Worker-side replica of a sharded table with a device-driven delta exchange (sender-side combining).
 
-``ReplicaCache(table)`` pulls a full local copy of ``table`` (row index == id).  Fused kernels train
-against ``replica.table_c`` (a single-shard ``ShardTable`` over local HBM); every ``sync_every`` calls
-of :meth:`after_step` a background stream runs ``fps_cache_sync``:
+``ReplicaCache(table)`` keeps a full local copy of ``table`` laid out **owner-major**: segment ``o``
+holds the rows of PS shard ``o`` in slot order, so segment ``o`` is the per-destination send buffer of
+the reference's batching senders (M/common/CombinationLogic.scala:12-33,
+M/client/sender/CombinationWorkerSender.scala:9-36).  Fused kernels train against
+``replica.table_c`` (the master's ``id -> (owner, slot)`` map with every "shard" in local HBM).
 
-  phase A: push ``replica - base`` to the master shards (one REDG per changed 16-byte chunk),
-           ``base <- value read``;
-  phase B: ``replica += master - base`` (the other workers' contributions, local REDG),
-           ``base <- master``.
+After every micro-batch two kernels run on a high-priority side stream (``ops/csrc/fps_replica.cu``):
 
-The invariant ``replica - base == local updates not yet pushed`` makes the exchange safe against
-concurrently running training kernels; nothing is lost, nothing needs a barrier, and a row crosses
-NVLink once per exchange instead of once per update.  This is the aggregated form of the reference's
-count / timer batching senders (M/common/CombinationLogic.scala) -- see DESIGN.md §2.1.
+* ``fps_flush_policy`` -- the **device-side** CountLogic / TimerLogic (CountLogic.scala:5-29,
+  TimerLogic.scala:6-51): per destination, "messages buffered >= count" and / or "``globaltimer``
+  deadline passed", combined with OR (``require="any"``) or AND (``"all"``).  The message counters
+  are fed on the device by the bucket histogram of the training step; no host clock is involved.
+* ``fps_replica_exchange`` -- for the flagged destinations: push ``replica - base`` (REDG over
+  NVLink), fold ``master - base`` (the other workers' pushes) into the replica, ``base <- master +
+  pushed delta``.  A few CTAs stream the segments with TMA bulk copies through a shared-memory ring, so
+  the kernel runs *next to* the HBM-bound training kernel (which leaves those CTA slots free).
+
+The invariant ``replica - base == local updates not yet pushed`` holds element-wise whatever the
+training kernels do concurrently, so nothing is lost and nothing needs a barrier; a row crosses NVLink
+once per flush per direction instead of once per update.  Destinations are staggered across steps and
+ranks (``(o - rank) % sync_every``) so the links stay evenly busy.  See DESIGN.md §2.1.
 """
 from __future__ import annotations
 
 import os
-import time
 from typing import List, Optional
 
 import torch
@@ -29,82 +36,152 @@ from .sharded_table import ShardedTable
 
 class ReplicaCache:
     def __init__(self, table: ShardedTable, sync_every: int = 4, sync_interval_ms: Optional[float] = None,
-                 require: str = "any", exchange_ctas: Optional[int] = None, overlap_steps: int = 2):
-        """Exchange trigger = the reference's combinable conditions (CountLogic / TimerLogic,
-        CombinationWorkerSender): ``sync_every`` micro-batches (count), ``sync_interval_ms`` since the
-        last exchange (timer), combined with ``require="any"`` (OR, default) or ``"all"`` (AND)."""
-        self.table = table
-        self.sync_every = max(1, int(sync_every))
-        # optional co-scheduling: confine the exchange kernel to `exchange_ctas` CTAs per SM and let the
-        # training kernels of the next `overlap_steps` micro-batches leave that many slots free
-        # (`reserve()`).  Default 0 = uncoordinated full-size grids: measured faster (N=1, exchange every
-        # 4 steps: 0.615 ms/step vs 0.666 / 0.661 with 1 / 2 reserved CTAs) -- a full-width exchange
-        # finishes in ~0.2 ms, a confined one slows training for longer than that.
-        if exchange_ctas is None:
-            exchange_ctas = int(os.environ.get("FPS_EXCHANGE_CTAS", "0"))
-        self.exchange_ctas = max(0, int(exchange_ctas))
-        self.overlap_steps = int(os.environ.get("FPS_EXCHANGE_OVERLAP_STEPS", overlap_steps))
-        self._steps_after_exchange = 1 << 30
-        self.sync_interval = None if sync_interval_ms is None else float(sync_interval_ms) / 1000.0
+                 require: str = "any", flush_count: Optional[int] = None,
+                 exchange_ctas: Optional[int] = None, stages: Optional[int] = None,
+                 stagger: bool = True, max_outstanding: int = 2):
+        """Flush trigger = the reference's combinable conditions: ``flush_count`` messages buffered for
+        a destination (CountLogic; default: what ``sync_every`` micro-batches send to one destination),
+        ``sync_interval_ms`` since the destination's last flush (TimerLogic, device ``globaltimer``),
+        combined with ``require="any"`` (OR) or ``"all"`` (AND)."""
         if require not in ("any", "all"):
             raise ValueError("require must be 'any' or 'all'")
-        self.require = require
-        self._last_sync = time.monotonic()
+        self.table = table
+        self.sync_every = max(1, int(sync_every))
+        self.flush_count = None if flush_count is None else int(flush_count)
+        self.interval_ns = 0 if sync_interval_ms is None else int(float(sync_interval_ms) * 1e6)
+        self.require_all = require == "all"
+        self.stagger = bool(stagger)
+        self.n_ctas = int(os.environ.get("FPS_EXCHANGE_CTAS", 32 if exchange_ctas is None else exchange_ctas))
+        self.stages = int(os.environ.get("FPS_EXCHANGE_STAGES", 4 if stages is None else stages))
+        self.sequential = os.environ.get("FPS_EXCHANGE_SEQUENTIAL", "0") == "1"
+        self.max_outstanding = max(1, int(max_outstanding))
         dev = table.cuda_device
+        self.world, self.rank, self.rps = table.world, table.rank, table.rows_per_shard
         with torch.cuda.device(table.device):
-            n_pad = table.rows_per_shard * table.world
-            self.cache = torch.empty((n_pad, table.stride), dtype=torch.float32, device=dev)
+            n_rows = self.rps * self.world
+            self.cache = torch.empty((n_rows, table.stride), dtype=torch.float32, device=dev)
             table.barrier()
-            native.pull_gather(table.table_c, torch.arange(n_pad, device=dev, dtype=torch.int64), self.cache)
+            # segment o, slot s  <-  master row of the id that lives at (owner o, slot s)
+            native.pull_gather(table.table_c, self._segment_ids(), self.cache)
             self.base = self.cache.clone()
-            self.table_c = native.local_table(self.cache, table.dim)
-            self.stream = torch.cuda.Stream(device=dev)
-        self._pending: List[torch.cuda.Event] = []
-        self._since_sync = 0
-        self.exchanges = 0
+            self.table_c = native.segment_table(self.cache, table.table_c)
+            self.state = torch.zeros(native.FLUSH_STATE_WORDS, dtype=torch.int64, device=dev)
+            self.stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._pending_events: List[torch.cuda.Event] = []
+        self._armed = False
+        self._since_flush = 0
+        self.steps = 0
         table.barrier()
 
-    def reserve(self) -> int:
-        """CTA slots per SM the next training kernel should leave free for an exchange in flight."""
-        return self.exchange_ctas if self._steps_after_exchange < self.overlap_steps else 0
-
-    def after_step(self) -> None:
-        self._since_sync += 1
-        self._steps_after_exchange += 1
-        count_hit = self._since_sync >= self.sync_every
-        if self.sync_interval is None:
-            fire = count_hit
+    # -- layout ---------------------------------------------------------------------------------
+    def _segment_ids(self) -> torch.Tensor:
+        dev = self.table.cuda_device
+        slots = torch.arange(self.rps, device=dev, dtype=torch.int64)
+        owners = torch.arange(self.world, device=dev, dtype=torch.int64)
+        if self.table.mode == native.PART_HASH:
+            ids = slots[None, :] * self.world + owners[:, None]
         else:
-            timer_hit = time.monotonic() - self._last_sync >= self.sync_interval
-            fire = (count_hit or timer_hit) if self.require == "any" else (count_hit and timer_hit)
-        if fire:
-            self.exchange()
+            ids = owners[:, None] * self.table.div + slots[None, :]
+        return ids.reshape(-1).contiguous()
 
-    def exchange(self) -> None:
-        """Start one delta exchange on the background stream (overlaps later training kernels)."""
+    def row_index(self, ids: torch.Tensor) -> torch.Tensor:
+        """Replica row of each id (owner-major)."""
+        ids = ids.to(torch.int64)
+        if self.table.mode == native.PART_HASH:
+            return (ids % self.world) * self.rps + ids // self.world
+        owner = torch.clamp(ids // self.table.div, max=self.world - 1)
+        return owner * self.rps + (ids - owner * self.table.div)
+
+    def rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """Current replica values of ``ids`` (tests / debugging)."""
+        return self.cache[self.row_index(ids), : self.table.dim]
+
+    @property
+    def pending(self) -> torch.Tensor:
+        """int64 ``[world]`` device counters: messages buffered per destination (fed by the bucket
+        histogram kernel of the training step, consumed by the policy kernel)."""
+        return self.state[: self.world]
+
+    def reserve_total(self) -> int:
+        """CTA slots the training kernel must leave free for the exchange running next to it."""
+        return self.n_ctas
+
+    # -- policy ---------------------------------------------------------------------------------
+    def _arm(self, n_records: int) -> None:
+        """First micro-batch: derive the count threshold from the batch size and stagger the
+        destinations ((o - rank) % sync_every micro-batches of head start)."""
+        per_dest = max(1, int(n_records) // self.world)
+        if self.flush_count is None:
+            self.flush_count = max(1, int((self.sync_every - 0.5) * per_dest))
+        if self.stagger and self.sync_every > 1:
+            head = [((o - self.rank) % self.sync_every) * per_dest for o in range(self.world)]
+            self.state[: self.world] += torch.tensor(head, dtype=torch.int64, device=self.state.device)
+        self._armed = True
+
+    def after_step(self, n_records: int, fed: bool = False) -> None:
+        """Call once per micro-batch, BEFORE launching the training kernel of that micro-batch (the
+        exchange CTAs then get their slots first).  ``fed``: the per-destination counters were already
+        incremented on the device (``native.bucket_by_item(..., pending=replica.pending)``)."""
+        if not self._armed:
+            self._arm(n_records)
+        dev = self.table.cuda_device
+        cur = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)                      # counters of this micro-batch are visible after this point
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            native.flush_policy(self.state, self.world, count_max=self.flush_count,
+                                interval_ns=self.interval_ns, require_all=self.require_all,
+                                add_uniform=0 if fed else max(1, int(n_records) // self.world))
+            native.replica_exchange(self.table.table_c, self.cache, self.base, state=self.state,
+                                    n_ctas=self.n_ctas, n_stages=self.stages, sequential=self.sequential)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._pending_events.append(done)
+        if len(self._pending_events) > self.max_outstanding:   # bounded staleness / run-ahead
+            cur.wait_event(self._pending_events.pop(0))
+        self.steps += 1
+        self._since_flush += 1
+        METRICS.inc("replica_policy_evals")
+
+    def exchange(self, wide: bool = True) -> None:
+        """Flush every destination now (force) on the side stream; does not block the current stream."""
         dev = self.table.cuda_device
         cur = torch.cuda.current_stream(dev)
         ev = torch.cuda.Event()
         ev.record(cur)
-        self.stream.wait_event(ev)                    # include everything trained so far
+        self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
-            native.cache_sync(self.table.table_c, self.cache, self.base, self.exchange_ctas)
+            native.flush_policy(self.state, self.world, force=True)
+            n = 2 * native.sm_count(self.table.device) if wide else self.n_ctas
+            native.replica_exchange(self.table.table_c, self.cache, self.base, state=self.state,
+                                    n_ctas=n, n_stages=self.stages)
             done = torch.cuda.Event()
             done.record(self.stream)
-        self._pending.append(done)
-        if len(self._pending) > 2:                    # at most two exchanges outstanding
-            cur.wait_event(self._pending.pop(0))
-        self._since_sync = 0
-        self._steps_after_exchange = 0
-        self._last_sync = time.monotonic()
-        self.exchanges += 1
+        self._pending_events.append(done)
+        self._since_flush = 0
         METRICS.inc("replica_exchanges")
 
     def flush(self) -> None:
         """Push every pending local delta to the masters and make the current stream wait for it."""
-        if self._since_sync > 0:
+        if self._since_flush > 0 or self._pending_events:
             self.exchange()
         cur = torch.cuda.current_stream(self.table.cuda_device)
-        for ev in self._pending:
+        for ev in self._pending_events:
             cur.wait_event(ev)
-        self._pending = []
+        self._pending_events = []
+
+    def refresh(self) -> None:
+        """Quiesce: after this (collective) call the master holds every rank's deltas and every
+        replica equals the master."""
+        self._since_flush = max(self._since_flush, 1)
+        self.flush()
+        self.table.barrier()
+        self._since_flush = 1
+        self.flush()
+        self.table.barrier()
+
+    def flush_counts(self) -> List[int]:
+        """Number of flushes per destination so far (device counters)."""
+        lo = native.FLUSH_COUNT
+        return self.state[lo: lo + self.world].tolist()

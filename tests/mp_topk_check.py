@@ -11,11 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
-    lr_ = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(lr_)
-    dev = torch.device("cuda", lr_)
-    dist.init_process_group("nccl", device_id=dev)
+    from tests.mp_util import init_dist
+    rank, world, dev, shared = init_dist()
     from fps_b200.models.mf.device_topk import DistributedTopK
     from fps_b200.store.sharded_table import ShardedTable
 
@@ -27,10 +24,8 @@ def main():
     q = torch.randint(0, nu, (300,), generator=torch.Generator().manual_seed(7)).to(dev)   # same on all ranks
     sc, ids = DistributedTopK(users, local_items, local_ids).topk(q, K)
     # reference: gather every rank's items, exact fp32 scores
-    all_items = [torch.empty_like(local_items) for _ in range(world)]
-    all_ids = [torch.empty_like(local_ids) for _ in range(world)]
-    dist.all_gather(all_items, local_items); dist.all_gather(all_ids, local_ids)
-    items = torch.cat(all_items); gids = torch.cat(all_ids)
+    from tests.mp_util import all_gather_cat
+    items = all_gather_cat(local_items); gids = all_gather_cat(local_ids)
     exact = users.pull(q) @ items.T
     ref = torch.topk(exact, K, dim=1)
     ref_ids = gids[ref.indices]

@@ -381,28 +381,90 @@ def test_device_mf_with_user_memory_skips_voided_records(dev):
     m.check_finite(); m.close(); m2.close()
 
 
-def test_replica_exchange_count_and_timer_triggers(dev):
-    """Count / timer / any / all exchange conditions (CountLogic, TimerLogic, CombinationLogic)."""
+def test_replica_flush_policy_count_timer_any_all_on_device(dev):
+    """Count / timer / OR / AND flush conditions evaluated ON THE DEVICE per destination
+    (CountLogic.scala:5-29, TimerLogic.scala:6-51, CombinationLogic.scala:12-33)."""
     import time
     from fps_b200.store.replica_cache import ReplicaCache
     from fps_b200.store.sharded_table import ShardedTable
 
     t = ShardedTable(500, 16, seed=1)
-    rc = ReplicaCache(t, sync_every=3)
+    rc = ReplicaCache(t, flush_count=300, stagger=False)       # count only: 100 messages per step
     for _ in range(7):
-        rc.after_step()
-    assert rc.exchanges == 2
-    rc = ReplicaCache(t, sync_every=1000, sync_interval_ms=20)
-    rc.after_step(); assert rc.exchanges == 0
-    time.sleep(0.03); rc.after_step(); assert rc.exchanges == 1
-    rc = ReplicaCache(t, sync_every=2, sync_interval_ms=20, require="all")
-    rc.after_step(); rc.after_step(); assert rc.exchanges == 0      # count reached, timer not yet
-    time.sleep(0.03); rc.after_step(); assert rc.exchanges == 1
-    rc.cache[7, :16] += 1.0                                          # a local update ...
-    rc.exchange(); rc.flush(); torch.cuda.synchronize()
+        rc.after_step(100)
+    torch.cuda.synchronize()
+    assert rc.flush_counts() == [2]                             # fired at 300 and 600 messages
+    assert int(rc.pending[0]) == 100                            # 700 - 2 * 300
+    rc = ReplicaCache(t, flush_count=10 ** 9, sync_interval_ms=20, stagger=False)   # timer only
+    rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [0]
+    time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
+    rc = ReplicaCache(t, flush_count=2, sync_interval_ms=20, require="all", stagger=False)
+    rc.after_step(1); rc.after_step(1); torch.cuda.synchronize()
+    assert rc.flush_counts() == [0]                             # count reached, deadline not yet
+    time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
+    # a local update reaches the master on flush, and only then
     ids = torch.tensor([7], device=dev)
-    torch.testing.assert_close(t.pull(ids)[0, :16], rc.cache[7, :16])  # ... reaches the master on flush
+    before = t.pull(ids)[0, :16].clone()
+    rc.cache[rc.row_index(ids)[0], :16] += 1.0
+    torch.cuda.synchronize()
+    torch.testing.assert_close(t.pull(ids)[0, :16], before)
+    rc.flush(); torch.cuda.synchronize()
+    torch.testing.assert_close(t.pull(ids)[0, :16], before + 1.0)
+    torch.testing.assert_close(rc.rows(ids)[0], before + 1.0)
+    assert torch.equal(rc.base, rc.cache)
     t.close()
+
+
+@pytest.mark.parametrize("dim,n", [(64, 20011), (300, 1777), (3, 513)])
+def test_replica_exchange_conserves_every_delta_single_rank(dev, dim, n):
+    """Pushes into the replica while exchanges run on the side stream: afterwards the master holds
+    init + every delta exactly once, replica == master == base (SimplePSLogic.scala:16-25 semantics
+    through the batching path)."""
+    from fps_b200.ops import native
+    from fps_b200.store.replica_cache import ReplicaCache
+    from fps_b200.store.sharded_table import ShardedTable
+
+    t = ShardedTable(n, dim, seed=3, init_range=(-1, 1))
+    all_ids = torch.arange(n, device=dev)
+    init = t.pull(all_ids).clone()
+    rc = ReplicaCache(t, sync_every=2)
+    g = torch.Generator(device="cpu").manual_seed(dim)
+    total = torch.zeros(n, dim, device=dev)
+    for step in range(9):
+        ids = torch.randint(0, n, (4000,), generator=g).to(dev)
+        delta = torch.randn(4000, dim, generator=g).to(dev)
+        rc.after_step(4000)                                     # exchange overlaps the push below
+        native.push_add(rc.table_c, ids, delta)
+        total.index_add_(0, ids, delta)
+    rc.refresh(); torch.cuda.synchronize()
+    torch.testing.assert_close(t.pull(all_ids), init + total, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rc.rows(all_ids), init + total, rtol=1e-5, atol=1e-5)
+    assert torch.equal(rc.base, rc.cache)
+    t.close()
+
+
+def test_bucket_by_replica_row_and_destination_feed(dev):
+    """Owner-major bucketing: bucket = ((item % G) * rps + item // G) >> shift, and the histogram kernel
+    feeds the per-destination message counters of the device-side flush policy."""
+    from fps_b200.ops import native
+
+    n, n_items, G, shift = 50_001, 6000, 4, 8
+    rps = -(-n_items // G)
+    g = torch.Generator().manual_seed(5)
+    users = torch.randint(0, 1 << 20, (n,), generator=g, dtype=torch.int32).to(dev)
+    items = torch.randint(0, n_items, (n,), generator=g, dtype=torch.int32).to(dev)
+    ratings = torch.randint(0, 64, (n,), generator=g).float().to(dev)
+    scratch = torch.zeros(2 * native.BUCKET_MAX, dtype=torch.int32, device=dev)
+    pending = torch.zeros(G, dtype=torch.int64, device=dev)
+    nb = -(-(rps * G) >> shift)
+    rec = native.pack_ratings(users, items, ratings)
+    out, _, _ = native.bucket_by_item(rec, None, None, shift, nb, scratch, num_shards=G,
+                                      rows_per_shard=rps, pending=pending)
+    assert torch.equal(torch.sort(out).values, torch.sort(rec).values)
+    it = (out >> 16) & 0x3FFFFF
+    b = ((it % G) * rps + it // G) >> shift
+    assert (b[1:] >= b[:-1]).all()
+    assert torch.equal(pending, torch.bincount(items.long() % G, minlength=G))
 
 
 @pytest.mark.parametrize("packed", [False, True])

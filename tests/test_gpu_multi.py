@@ -1,35 +1,42 @@
-"""Launch the multi-rank device checks under torchrun when >= 2 GPUs are visible."""
+"""Launch the multi-rank device checks under torchrun.
+
+With >= 2 GPUs every rank gets its own GPU (NCCL control plane, NVLink data plane).  On a single-GPU
+box the same checks run with the ranks SHARING the GPU (gloo control plane; CUDA IPC maps the other
+processes' shards exactly like peer GPUs), so the multi-rank logic -- fabric, one-sided pull/push,
+replica exchange, distributed top-K -- is exercised by every ``pytest -m gpu`` run."""
 import os
 import subprocess
-import sys
 
 import pytest
 import torch
 
+from tests.mp_util import REPO, launch_cmd
+
 pytestmark = pytest.mark.gpu
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.multigpu
-def test_two_rank_fabric_and_fused_step():
+def _run(script: str, world: int, port: int, ok: str, timeout: int = 900):
+    env = dict(os.environ)
+    if torch.cuda.device_count() < world:
+        env["FPS_SHARE_GPU"] = "1"
+    r = subprocess.run(launch_cmd(script, world, port), cwd=REPO, capture_output=True, text=True,
+                       timeout=timeout, env=env)
+    assert r.returncode == 0 and ok in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def _world(prefer: int = 4) -> int:
     n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    world = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29617",
-           os.path.join(REPO, "tests", "mp_device_check.py")]
-    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MP_DEVICE_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    return 2 if n < prefer else prefer
 
 
-@pytest.mark.multigpu
-def test_two_rank_distributed_topk():
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29618",
-           os.path.join(REPO, "tests", "mp_topk_check.py")]
-    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MP_TOPK_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+def test_multi_rank_fabric_and_fused_step():
+    _run("mp_device_check.py", _world(), 29617, "MP_DEVICE_CHECK_OK")
+
+
+def test_multi_rank_distributed_topk():
+    _run("mp_topk_check.py", 2, 29618, "MP_TOPK_CHECK_OK")
+
+
+def test_multi_rank_replica_exchange_conservation_and_convergence():
+    _run("mp_replica_check.py", _world(), 29619, "MP_REPLICA_CHECK_OK")

@@ -38,7 +38,7 @@ def test_kernel_library_builds_and_is_current():
     import ctypes
     lib = ctypes.CDLL(str(path))
     for sym in ["fps_mf_sgd_fused", "fps_mf_sgd_tma", "fps_topk_mma", "fps_pa_step", "fps_sketch_update",
-                "fps_server_loop_launch", "fps_client_issue", "fps_client_collect", "fps_cache_sync",
+                "fps_server_loop_launch", "fps_client_issue", "fps_client_collect", "fps_replica_exchange", "fps_flush_policy",
                 "fps_pull_gather", "fps_push_add", "fps_push_assign", "fps_pull_dot", "fps_init_rows",
                 "fps_bloom_query", "fps_rings_preload"]:
         assert hasattr(lib, sym), sym
