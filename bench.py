@@ -58,6 +58,13 @@ def parse():
     p.add_argument("--update-rule", default="parity", choices=["parity", "plain"],
                    help="parity: the reference's e = sigmoid(r - u.v) (SGDUpdater.scala:8; always positive, so "
                         "the squared error drifts up by design); plain: e = r - u.v (textbook SGD, loss falls)")
+    p.add_argument("--quality-updates-per-user", type=float, default=400.0,
+                   help="convergence gate (outside the timed regions): total update budget = this x users, the "
+                        "same synthetic low-rank stream trained by the replica mode, the direct one-sided mode "
+                        "and ONE worker alone; 0 disables")
+    p.add_argument("--quality-lr", type=float, default=0.05)
+    p.add_argument("--quality-init", type=float, default=0.05)
+    p.add_argument("--no-direct", action="store_true", help="skip the direct one-sided mode measurement (N > 1)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: reg = register-staged loads at full occupancy)")
     return p.parse_args()
@@ -118,12 +125,82 @@ class ClockSampler:
                 "samples": len(inside), "window": window, "reasons": reasons}
 
 
+def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN):
+    """Same synthetic low-rank rating stream, same update budget, plain-residual SGD: N workers in
+    replica mode, N workers in direct one-sided mode, and ONE worker alone; held-out RMSE of each."""
+    import torch
+    import torch.distributed as dist
+    from fps_b200.utils.synthetic import lowrank_ratings
+
+    budget = a.quality_updates_per_user * a.users
+    steps = max(8, int(budget / (a.batch * world)))
+    init = a.quality_init
+
+    def batch_of(rid, step):
+        g = torch.Generator(device=dev).manual_seed(7919 * step + rid + 1)
+        u = torch.randint(0, a.users // world, (a.batch,), generator=g, device=dev, dtype=torch.int32) * world + rid
+        i = torch.randint(0, a.items, (a.batch,), generator=g, device=dev, dtype=torch.int32)
+        return u, i, lowrank_ratings(u, i)
+
+    gh = torch.Generator(device=dev).manual_seed(99991)
+    hu = torch.randint(0, a.users, (1 << 20,), generator=gh, device=dev, dtype=torch.int32)
+    hi = torch.randint(0, a.items, (1 << 20,), generator=gh, device=dev, dtype=torch.int32)
+    hr = lowrank_ratings(hu, hi)
+
+    def rmse(model, w, r):
+        mine = (hu % w) == r
+        pred = model.predict(hu[mine], hi[mine])
+        t = torch.stack([((hr[mine] - pred) ** 2).sum().double(), mine.sum().double()])
+        if w > 1:
+            if shared_gpu:
+                h = t.cpu(); dist.all_reduce(h); t = h
+            else:
+                dist.all_reduce(t)
+        return float((t[0] / t[1]).sqrt())
+
+    kw = dict(learning_rate=a.quality_lr, range_min=-init, range_max=init, seed=4321, err_mode=ERR_PLAIN)
+    out = {"update_rule": "plain residual e = r - u.v", "lr": a.quality_lr, "init": init,
+           "data": "rank-8 synthetic ratings (utils/synthetic.py), std 0.5", "steps_per_worker": steps,
+           "updates": steps * a.batch * world, "rmse_untrained": float(hr.std())}
+    if world > 1:
+        for mode, cache in (("replica", True), ("direct", False)):
+            m = DeviceOnlineMF(a.users, a.items, a.factors, item_cache=cache, sync_every=a.sync_every, **kw)
+            for s in range(steps):
+                m.step(*batch_of(rank, s))
+            m.refresh()
+            m.check_finite()
+            out["rmse_" + mode] = rmse(m, world, rank)
+            m.barrier(); m.close(); del m
+        groups = [dist.new_group([r]) for r in range(world)]
+        solo = DeviceOnlineMF(a.users, a.items, a.factors, group=groups[rank], **kw) if rank == 0 else None
+    else:
+        solo = DeviceOnlineMF(a.users, a.items, a.factors, **kw)
+    ref = torch.zeros(1, dtype=torch.float64, device="cpu" if shared_gpu else dev)
+    if rank == 0:
+        for s in range(steps):
+            for rid in range(world):
+                solo.step(*batch_of(rid, s))
+        solo.check_finite()
+        ref[0] = rmse(solo, 1, 0)
+        solo.close()
+    if world > 1:
+        dist.all_reduce(ref)
+    out["rmse_single_worker"] = float(ref[0])
+    if world > 1:
+        out["replica_vs_single"] = out["rmse_replica"] / out["rmse_single_worker"]
+        out["direct_vs_single"] = out["rmse_direct"] / out["rmse_single_worker"]
+        out["within_2pct"] = bool(abs(out["replica_vs_single"] - 1) <= 0.02 and
+                                  abs(out["rmse_replica"] / out["rmse_direct"] - 1) <= 0.02)
+    return out
+
+
 def main():
     a = parse()
     if a.impl == "reference":
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "reference is Scala 2.11 / Apache Flink 1.4 (no setup.py/pyproject: pip "
-                          "reports 'not installable'); image has no JVM, sbt or network"}))
+        if int(os.environ.get("RANK", "0")) == 0:      # under torch.distributed.run: one line, from rank 0
+            print(json.dumps({"impl": "reference", "n_gpus": a.gpus, "unavailable":
+                              "reference is Scala 2.11 / Apache Flink 1.4 (no setup.py/pyproject: pip "
+                              "reports 'not installable'); image has no JVM, sbt or network"}), flush=True)
         return 0
 
     import torch
@@ -134,13 +211,26 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != a.gpus and world > 1:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
+    n_dev = torch.cuda.device_count()
+    shared_gpu = world > 1 and (os.environ.get("FPS_SHARE_GPU") == "1" or n_dev < world)
+    local_rank = local_rank % max(n_dev, 1) if shared_gpu else local_rank
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     saved_stdout = os.dup(1)
     os.dup2(2, 1)          # NCCL prints its version banner on stdout; rank 0 must print ONE JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        if shared_gpu:     # functional runs only: ranks share a GPU, gloo control plane, CUDA-IPC data plane
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cpu" if shared_gpu else dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     from fps_b200.ops import native
     from fps_b200.models.mf.device import DeviceOnlineMF, ERR_PLAIN, ERR_SIGMOID
@@ -198,10 +288,7 @@ def main():
     launches = native.launch_count() - launches0
     windows.append((w0, time.time()))
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms)
     model.check_finite()
 
     # ---- end to end through the public API -----------------------------------------------------
@@ -223,15 +310,48 @@ def main():
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     windows.append((w0, time.time()))
-    clocks = sampler.stop(windows) if rank == 0 else None
     e2e_ms = max(e0.elapsed_time(e1), wall_ms)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
+    e2e_ms_max = max_over_ranks(e2e_ms)
     assert n_res == a.steps
     h2d = sum(x.numel() * x.element_size() for x in host[0])
     barrier()
+
+    # ---- the north-star path on the record: direct one-sided mode (every update pulls its item row from
+    #      the owner and pushes the delta back inside the fused kernel; no replica) -----------------------
+    direct = None
+    if world > 1 and a.impl == "fps_b200" and not a.no_direct and getattr(model, "item_cache", False):
+        dm = DeviceOnlineMF(a.users, a.items, a.factors, learning_rate=a.lr, pull_limit=a.pull_limit,
+                            seed=1234, err_mode=ERR_SIGMOID if a.update_rule == "parity" else ERR_PLAIN,
+                            kernel=a.kernel, item_cache=False)
+        for s in range(a.warmup):
+            dm.step(*devb[s % len(devb)])
+        barrier()
+        w0 = time.time()
+        e0.record()
+        for s in range(a.steps):
+            dm.step(*devb[(a.warmup + s) % len(devb)])
+        e1.record()
+        torch.cuda.synchronize()
+        d_ms = max_over_ranks(e0.elapsed_time(e1))
+        windows.append((w0, time.time()))
+        dm.check_finite()
+        barrier()
+        dm.close()
+        del dm
+        direct = {"value": a.steps * a.batch * world / (d_ms / 1e3), "unit": "updates/s",
+                  "ms_per_step": d_ms / a.steps,
+                  "note": "item_cache off: per-update one-sided pull (peer LDG.128) + push (REDG.ADD.F32x4) "
+                          "over NVLink inside the fused kernel; link bound for remote rows"}
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    # ---- convergence gate (outside every timed region) ---------------------------------------------
+    quality = None
+    if a.impl == "fps_b200" and a.quality_updates_per_user > 0:
+        try:
+            quality = quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN)
+        except Exception as exc:     # the headline line must be printed whatever happens here
+            quality = {"error": f"{type(exc).__name__}: {exc}"}
+        barrier()
 
     if rank == 0:
         total_updates = a.steps * a.batch * world
@@ -261,7 +381,9 @@ def main():
                                        "reported mse drifts upward by design; --update-rule plain trains with "
                                        "e=r-u.v at the same speed" if a.update_rule == "parity"
                                        else "plain residual e=r-u.v"),
-                       "precision_note": "fp32 tables and math (reference: fp64 on the JVM)"},
+                       "precision_note": "fp32 tables and math (reference: fp64 on the JVM)",
+                       "quality": quality},
+            "value_direct": direct,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms_max / a.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
