@@ -55,6 +55,18 @@ def _result(model: DeviceOnlineMF, seen_users: Optional[set]) -> ResultStream:
     return rs
 
 
+def _agree_max(num_users: int, num_items: int, group):
+    """Sizes derived from a rank's LOCAL partition differ between ranks; every rank must build the same
+    table geometry (peer row addresses are computed from it), so take the maximum over the job."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return num_users, num_items
+    sizes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(sizes, (int(num_users), int(num_items)), group=group)
+    return max(s[0] for s in sizes), max(s[1] for s in sizes)
+
+
 def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learningRate=0.01,
                         negativeSampleRate=0, pullLimit=0, seed=0, plain_residual=False,
                         numUsers: Optional[int] = None, numItems: Optional[int] = None,
@@ -63,13 +75,15 @@ def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learn
     recs = None
     if numUsers is None or numItems is None:
         recs = list(src.collect() if hasattr(src, "collect") else src)
-        numUsers = 1 + max(r.user for r in recs)
-        numItems = 1 + max(r.item for r in recs)
+        numUsers = 1 + max((r.user for r in recs), default=0)
+        numItems = 1 + max((r.item for r in recs), default=0)
         src = recs
-    # the reference's default pullLimit (1600) is a JVM-queue bound; on the device tier 0 means
-    # "as many row slots in flight as the GPU holds" and an explicit value bounds the rows in flight
+        numUsers, numItems = _agree_max(numUsers, numItems, group)
+    # pullLimit: None or 0 = as many row slots in flight as the GPU holds; any positive value bounds the
+    # rows in flight on the device (the reference's 1600 default is a JVM-queue bound -- pass it
+    # explicitly if that is what is wanted)
     model = DeviceOnlineMF(numUsers, numItems, numFactors, rangeMin, rangeMax, learningRate,
-                           negativeSampleRate, pull_limit=pullLimit if pullLimit and pullLimit != 1600 else 0,
+                           negativeSampleRate, pull_limit=int(pullLimit or 0),
                            group=group, seed=seed, err_mode=ERR_PLAIN if plain_residual else ERR_SIGMOID,
                            track_touched=True,
                            user_memory=min(int(userMemory), 256) if negativeSampleRate > 0 else 0)
@@ -206,7 +220,7 @@ def ps_online_learner_and_generator_device(src, numFactors=10, rangeMin=-0.001, 
     if numItems is None:
         numItems = 1 + max(r.item for r in recs)
     model = DeviceOnlineMF(numUsers, numItems, numFactors, rangeMin, rangeMax, learningRate,
-                           negativeSampleRate, pull_limit=pullLimit if pullLimit and pullLimit != 500 else 0,
+                           negativeSampleRate, pull_limit=int(pullLimit or 0),
                            group=group, seed=seed, err_mode=ERR_PLAIN if plain_residual else ERR_SIGMOID,
                            item_cache=False, user_memory=min(max(userMemory, 0), 256) if negativeSampleRate else 0)
     dev = model.cuda_device

@@ -86,14 +86,15 @@ class PSOfflineMatrixFactorizationWorker(CtorFork, WorkerLogic):
 
 def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: float = 0.01,
                 learningRate: float = 0.01, negativeSampleRate: int = 0, userMemory: int = 128,
-                iterations: int = 10, pullLimit: int = 1600, workerParallelism: int = 1,
+                iterations: int = 10, pullLimit: Optional[int] = None, workerParallelism: int = 1,
                 psParallelism: int = 1, iterationWaitTime: float = 10000, seed: Optional[int] = None,
                 plain_residual: bool = False, shuffle: bool = False, backend: str = "local",
                 **device_kw):
+    hostPullLimit = 1600 if pullLimit is None else pullLimit   # reference default (JVM queue bound)
     if backend == "native":
         from .native_api import ps_mf_native
 
-        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
+        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, hostPullLimit, workerParallelism,
                             psParallelism, seed or 0, plain_residual, epochs=iterations,
                             negativeSampleRate=negativeSampleRate, userMemory=userMemory)
     if backend == "device":
@@ -116,7 +117,7 @@ def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: fl
     worker = addPullLimiter(
         PSOfflineMatrixFactorizationWorker(numFactors, rangeMin, rangeMax, learningRate,
                                            negativeSampleRate, userMemory, iterations, seed,
-                                           plain_residual, shuffle), pullLimit)
+                                           plain_residual, shuffle), hostPullLimit)
     return transform(ratings, worker, paramInit, vectorSum, workerParallelism, psParallelism,
                      iterationWaitTime)
 

@@ -105,16 +105,17 @@ class PSOnlineMatrixFactorizationWorker(WorkerLogic):
 
 def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: float = 0.01,
                learningRate: float = 0.01, negativeSampleRate: int = 0, userMemory: int = 128,
-               pullLimit: int = 1600, workerParallelism: int = 1, psParallelism: int = 1,
+               pullLimit: Optional[int] = None, workerParallelism: int = 1, psParallelism: int = 1,
                iterationWaitTime: float = 10000, seed: Optional[int] = None,
                plain_residual: bool = False, backend: str = "local", **device_kw):
     """Returns the stream of ``Left((userId, userVector))`` / ``Right((itemId, itemVector))``.
     ``backend="local"``: arbitrary-logic Python engine; ``"native"``: the same protocol on the C++ host
     engine (threads + SPSC rings, ``ops/csrc/fps_host.cpp``); ``"device"``: fused B200 kernels."""
+    hostPullLimit = 1600 if pullLimit is None else pullLimit   # reference default (JVM queue bound)
     if backend == "native":
         from .native_api import ps_mf_native
 
-        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, pullLimit, workerParallelism,
+        return ps_mf_native(src, numFactors, rangeMin, rangeMax, learningRate, hostPullLimit, workerParallelism,
                             psParallelism, seed or 0, plain_residual, epochs=1,
                             negativeSampleRate=negativeSampleRate, userMemory=userMemory)
     if backend == "device":
@@ -135,7 +136,7 @@ def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: flo
 
     workerLogic = addPullLimiter(
         PSOnlineMatrixFactorizationWorker(numFactors, rangeMin, rangeMax, learningRate, userMemory,
-                                          negativeSampleRate, seed, plain_residual), pullLimit)
+                                          negativeSampleRate, seed, plain_residual), hostPullLimit)
     serverLogic = SimplePSLogic(paramInit, vectorSum)
     partitioned = as_stream(src).partition_custom(lambda key, n: key % n, lambda r: r.user)
     return transform(partitioned, workerLogic, serverLogic, workerParallelism, psParallelism,

@@ -272,7 +272,7 @@ def psOnlineLearnerAndGenerator(src, numFactors: int = 10, rangeMin: float = -0.
                                 rangeMax: float = 0.001, learningRate: float = 0.01,
                                 negativeSampleRate: int = 0, userMemory: int = 65535, K: int = 100,
                                 workerK: int = 75, bucketSize: int = 100,
-                                pruningAlgorithm: LEMPPruningStrategy = LI(5, 2.5), pullLimit: int = 500,
+                                pruningAlgorithm: LEMPPruningStrategy = LI(5, 2.5), pullLimit: Optional[int] = None,
                                 workerParallelism: int = 4, psParallelism: int = 4,
                                 iterationWaitTime: float = 10000, seed: Optional[int] = None,
                                 plain_residual: bool = False, backend: str = "local", **device_kw):
@@ -290,7 +290,7 @@ def psOnlineLearnerAndGenerator(src, numFactors: int = 10, rangeMin: float = -0.
     worker = addPullLimiter(
         PSOnlineMatrixFactorizationAndTopKGeneratorWorker(
             negativeSampleRate, userMemory, workerK, bucketSize, pruningAlgorithm, workerParallelism,
-            initDesc, SGDUpdater(learningRate, plain_residual), seed), pullLimit)
+            initDesc, SGDUpdater(learningRate, plain_residual), seed), 500 if pullLimit is None else pullLimit)
     holder = {}
 
     def init(x):

@@ -11,7 +11,10 @@
 
 #define FPS_MAX_SHARDS 16
 
-enum FpsPartition : int { FPS_PART_HASH = 0, FPS_PART_RANGE = 1 };
+// HASH / RANGE are computed; LUT is a device lookup table id -> (owner << 40 | slot) that realises
+// arbitrary user partitioners (FPS:343 paramPartitioner) and interned opaque / string ids.
+enum FpsPartition : int { FPS_PART_HASH = 0, FPS_PART_RANGE = 1, FPS_PART_LUT = 2 };
+#define FPS_LUT_SLOT_MASK ((1ll << 40) - 1)
 
 struct ShardTable {
   float* base[FPS_MAX_SHARDS];          // peer-mapped base pointer per shard
@@ -24,6 +27,7 @@ struct ShardTable {
   int mode;    // FpsPartition
   int shard_shift;  // log2(num_shards) if it is a power of two, else -1 (fast hash locate)
   int pad_;
+  const long long* lut;  // FPS_PART_LUT: lut[id] = owner << 40 | slot (device memory, local to the reader)
 };
 
 // id -> (owner shard, slot).  Hash mode mirrors `abs(id.hashCode) % psParallelism`
@@ -34,6 +38,10 @@ __device__ __forceinline__ void fps_locate(const ShardTable& t, long long id, in
     long long a = id < 0 ? -id : id;
     owner = (int)(a % t.num_shards);
     slot = a / t.num_shards;
+  } else if (t.mode == FPS_PART_LUT) {
+    const long long e = t.lut[id];
+    owner = (int)(e >> 40);
+    slot = e & FPS_LUT_SLOT_MASK;
   } else {
     owner = (int)(id / t.div);
     if (owner >= t.num_shards) owner = t.num_shards - 1;
@@ -54,6 +62,10 @@ __device__ __forceinline__ float* fps_row32(const ShardTable& t, int id) {
       owner = a - slot * (unsigned)t.num_shards;
     }
     return t.base[owner] + (size_t)slot * (size_t)t.stride;
+  }
+  if (t.mode == FPS_PART_LUT) {
+    const long long e = t.lut[id];
+    return t.base[(int)(e >> 40)] + (size_t)(e & FPS_LUT_SLOT_MASK) * (size_t)t.stride;
   }
   unsigned owner = (unsigned)id / (unsigned)t.div;
   if (owner >= (unsigned)t.num_shards) owner = t.num_shards - 1;

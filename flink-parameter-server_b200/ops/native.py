@@ -18,6 +18,8 @@ from . import build as _build
 FPS_MAX_SHARDS = 16
 PART_HASH = 0
 PART_RANGE = 1
+PART_LUT = 2
+LUT_OWNER_SHIFT = 40
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -38,6 +40,7 @@ class ShardTableC(C.Structure):
         ("mode", C.c_int),
         ("shard_shift", C.c_int),
         ("pad_", C.c_int),
+        ("lut", C.c_void_p),
     ]
 
 

@@ -56,7 +56,7 @@ class ReplicaCache:
         self.sequential = os.environ.get("FPS_EXCHANGE_SEQUENTIAL", "0") == "1"
         self.max_outstanding = max(1, int(max_outstanding))
         dev = table.cuda_device
-        self.world, self.rank, self.rps = table.world, table.rank, table.rows_per_shard
+        self.world, self.rank, self.rps = table.n_shards, table.rank, table.rows_per_shard
         with torch.cuda.device(table.device):
             n_rows = self.rps * self.world
             self.cache = torch.empty((n_rows, table.stride), dtype=torch.float32, device=dev)

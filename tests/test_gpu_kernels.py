@@ -288,7 +288,8 @@ def test_item_cache_mode_single_gpu_matches_direct_mode(dev):
     m_cache = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, item_cache=True,
                              sync_every=2)
     V0 = m_cache.items.local.clone()
-    assert torch.equal(m_cache.cache[:ni], V0[:ni]) and torch.equal(m_cache.base, m_cache.cache)
+    rep = m_cache.replica
+    assert torch.equal(rep.cache[:ni], V0[:ni]) and torch.equal(rep.base, rep.cache)
     g = torch.Generator().manual_seed(1)
     for step in range(3):
         users = torch.randperm(nu, generator=g)[:b].int().cuda()
@@ -299,8 +300,8 @@ def test_item_cache_mode_single_gpu_matches_direct_mode(dev):
     torch.cuda.synchronize()
     torch.testing.assert_close(m_cache.users, m_direct.users, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(m_cache.items.local, m_direct.items.local, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(m_cache.cache[:ni], m_cache.items.local[:ni], rtol=1e-6, atol=1e-7)
-    torch.testing.assert_close(m_cache.base, m_cache.cache, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(m_cache.replica.cache[:ni], m_cache.items.local[:ni], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(m_cache.replica.base, m_cache.replica.cache, rtol=1e-6, atol=1e-7)
     m_direct.close(); m_cache.close()
 
 

@@ -21,7 +21,12 @@ def _run(script: str, world: int, port: int, ok: str, timeout: int = 900):
         env["FPS_SHARE_GPU"] = "1"
     r = subprocess.run(launch_cmd(script, world, port), cwd=REPO, capture_output=True, text=True,
                        timeout=timeout, env=env)
-    assert r.returncode == 0 and ok in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    if r.returncode != 0 or ok not in r.stdout:      # keep the full transcript for post-mortems
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(REPO, "gpurun_out", f"mp_fail_{script}.log"), "w") as f:
+            f.write(r.stdout + "\n=== stderr ===\n" + r.stderr)
+    err = [l for l in r.stderr.splitlines() if "Error" in l or "assert" in l.lower()]
+    assert r.returncode == 0 and ok in r.stdout, "\n".join(err[:12]) + r.stdout[-1500:] + r.stderr[-1500:]
     return r.stdout
 
 
