@@ -125,7 +125,7 @@ class ClockSampler:
                 "samples": len(inside), "window": window, "reasons": reasons}
 
 
-def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN):
+def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN, sync_list=None):
     """Same synthetic low-rank rating stream, same update budget, plain-residual SGD: N workers in
     replica mode, N workers in direct one-sided mode, and ONE worker alone; held-out RMSE of each."""
     import torch
@@ -163,8 +163,10 @@ def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN):
            "data": "rank-8 synthetic ratings (utils/synthetic.py), std 0.5", "steps_per_worker": steps,
            "updates": steps * a.batch * world, "rmse_untrained": float(hr.std())}
     if world > 1:
-        for mode, cache in (("replica", True), ("direct", False)):
-            m = DeviceOnlineMF(a.users, a.items, a.factors, item_cache=cache, sync_every=a.sync_every, **kw)
+        runs = [("direct", False, a.sync_every), ("replica", True, a.sync_every)]
+        runs += [(f"replica_sync{se}", True, se) for se in (sync_list or []) if se != a.sync_every]
+        for mode, cache, se in runs:
+            m = DeviceOnlineMF(a.users, a.items, a.factors, item_cache=cache, sync_every=se, **kw)
             for s in range(steps):
                 m.step(*batch_of(rank, s))
             m.refresh()
@@ -187,6 +189,9 @@ def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN):
         dist.all_reduce(ref)
     out["rmse_single_worker"] = float(ref[0])
     if world > 1:
+        for k in [k for k in out if k.startswith("rmse_replica_sync")]:
+            out[k.replace("rmse_", "") + "_vs_single"] = out[k] / out["rmse_single_worker"]
+        out["sync_every"] = a.sync_every
         out["replica_vs_single"] = out["rmse_replica"] / out["rmse_single_worker"]
         out["direct_vs_single"] = out["rmse_direct"] / out["rmse_single_worker"]
         out["within_2pct"] = bool(abs(out["replica_vs_single"] - 1) <= 0.02 and
@@ -382,6 +387,10 @@ def main():
                                        "e=r-u.v at the same speed" if a.update_rule == "parity"
                                        else "plain residual e=r-u.v"),
                        "precision_note": "fp32 tables and math (reference: fp64 on the JVM)",
+                       "exchange": ({"ctas": model.replica.n_ctas, "stages": model.replica.stages,
+                                     "sliced": model.replica.sliced, "own_shard_in_place": model.replica.own is not None,
+                                     "kernel_ms": model.replica.timing_summary()}
+                                    if getattr(model, "replica", None) is not None else None),
                        "quality": quality},
             "value_direct": direct,
             "clocks": clocks,

@@ -45,7 +45,7 @@ class DeviceOnlineMF:
                  sync_every: int = 4, user_memory: int = 0,
                  sync_interval_ms: Optional[float] = None, item_blocking: Optional[bool] = None,
                  block_bytes: int = 16 << 20, flush_count: Optional[int] = None,
-                 flush_require: str = "any"):
+                 flush_require: str = "any", replica_own_inplace: Optional[bool] = None):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -95,8 +95,10 @@ class DeviceOnlineMF:
         self.sync_every = max(1, int(sync_every))
         self.sync_interval_ms = sync_interval_ms
         self.flush_count, self.flush_require = flush_count, flush_require
+        self._own_inplace = replica_own_inplace
         self.replica = (ReplicaCache(self.items, self.sync_every, sync_interval_ms,
-                                     require=flush_require, flush_count=flush_count)
+                                     require=flush_require, flush_count=flush_count,
+                                     own_inplace=replica_own_inplace)
                         if self.item_cache else None)
         # ---- L2 blocking: deal each micro-batch into buckets of <= 16 MB of item rows (fps_bucket.cu) ----
         # only where the item rows are read from local HBM (single GPU, or the local replica)
@@ -272,7 +274,8 @@ class DeviceOnlineMF:
         self.items.barrier()
         if self.replica is not None:
             self.replica = ReplicaCache(self.items, self.sync_every, self.sync_interval_ms,
-                                        require=self.flush_require, flush_count=self.flush_count)
+                                        require=self.flush_require, flush_count=self.flush_count,
+                                        own_inplace=self._own_inplace)
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:

@@ -283,18 +283,38 @@ extern "C" int fps_mf_sgd_fused(const MfArgs* args, int id_bytes, int max_inflig
 // pull_dot:      score[i] = table[ids[i], :] . local[i, :]   (pull fused with the consumer)
 // One lane-group of LPR lanes per row, VPL chunks per lane, generic in dim via nvec bound.
 // ----------------------------------------------------------------------------------------
+// Device-side pull limiter (WL:196-250 as a credit counter): `credits[0]` holds the number of pulls that
+// may still be issued; a lane-group takes one credit before it touches the owner's memory and returns
+// it when the answer has been consumed (stored), so at most `pullLimit` row pulls are un-answered at any
+// time whatever the grid size.  `credits[1]` counts the stalls (acquisitions that had to wait).
+__device__ __forceinline__ void fps_credit_acquire(int* credits) {
+  bool stalled = false;
+  while (atomicSub(credits, 1) <= 0) {
+    atomicAdd(credits, 1);
+    stalled = true;
+    __nanosleep(128);
+  }
+  if (stalled) atomicAdd(credits + 1, 1);
+}
+
 template <typename IdT, int LPR>
 __global__ void __launch_bounds__(256)
     fps_pull_gather_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
-                           long long n, float* __restrict__ out, int out_stride, int touch) {
+                           long long n, float* __restrict__ out, int out_stride, int touch,
+                           int* __restrict__ credits) {
   const int lane = threadIdx.x & (LPR - 1);
   const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
   const long long n_groups = ((long long)gridDim.x * blockDim.x) / LPR;
   const int nvec = t.stride >> 2;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) & ~(LPR - 1)));
   for (long long i = group; i < n; i += n_groups) {
     const long long id = (long long)ids[i];
     const float* src = fps_row_t<IdT>(t, ids[i]);
     if (touch && lane == 0) fps_touch(t, id);
+    if (credits != nullptr) {
+      if (lane == 0) fps_credit_acquire(credits);
+      __syncwarp(gmask);
+    }
     for (int q = lane; q < nvec; q += LPR) {
       float4 v = fps_ld_row4(src + 4 * q);
       float* o = out + i * (long long)out_stride + 4 * q;
@@ -306,6 +326,10 @@ __global__ void __launch_bounds__(256)
         if (4 * q + 2 < out_stride) o[2] = v.z;
         if (4 * q + 3 < out_stride) o[3] = v.w;
       }
+    }
+    if (credits != nullptr) {
+      __syncwarp(gmask);                       // the answer has been consumed by every lane
+      if (lane == 0) atomicAdd(credits, 1);    // release the credit
     }
   }
 }
@@ -495,20 +519,23 @@ static inline int limit_grid(int grid, int lpr, int max_inflight_rows) {
   return grid < cap ? grid : cap;
 }
 
+// credits != nullptr: device credit counter (credits[0] must hold pullLimit, credits[1] counts stalls);
+// otherwise max_inflight_rows > 0 caps the grid (static variant of the limiter).
 extern "C" int fps_pull_gather(const ShardTable* t, const void* ids, int id_bytes, long long n,
                                float* out, int out_stride, int touch, int num_sms,
-                               int max_inflight_rows, cudaStream_t stream) {
+                               int max_inflight_rows, int* credits, cudaStream_t stream) {
   if (n <= 0) return 0;
-  if (use_wide(t, out_stride, touch) && max_inflight_rows <= 0)
+  if (use_wide(t, out_stride, touch) && max_inflight_rows <= 0 && credits == nullptr)
     return launch_wide<0>(t, ids, id_bytes, n, out, out_stride, 1.f, num_sms, stream);
   const int lpr = pick_lpr(t->stride >> 2);
-  const int grid = limit_grid(row_grid(n, lpr, num_sms), lpr, max_inflight_rows);
+  int grid = row_grid(n, lpr, num_sms);
+  if (credits == nullptr) grid = limit_grid(grid, lpr, max_inflight_rows);
   if (id_bytes == 4) {
     FPS_DISPATCH_LPR(fps_pull_gather_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, out,
-                     out_stride, touch)
+                     out_stride, touch, credits)
   } else {
     FPS_DISPATCH_LPR(fps_pull_gather_kernel, long long, lpr, grid, stream, *t,
-                     (const long long*)ids, n, out, out_stride, touch)
+                     (const long long*)ids, n, out, out_stride, touch, credits)
   }
   return (int)cudaGetLastError();
 }
@@ -563,3 +590,39 @@ extern "C" int fps_push_assign(const ShardTable* t, const void* ids, int id_byte
   return (int)cudaGetLastError();
 }
 
+
+// ----------------------------------------------------------------------------------------
+// K2 with PS output: table[ids[i], :] += delta[i, :] and out[i, :] = the value AFTER this update --
+// SimplePSLogic emits (id, newValue) on EVERY push (SimplePSLogic.scala:16-25).  Returning atomics
+// (one per element), so concurrent pushes to one id each see a distinct prefix sum.
+// ----------------------------------------------------------------------------------------
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+    fps_push_add_fetch_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,
+                              long long n, const float* __restrict__ delta, int delta_stride,
+                              float* __restrict__ out, int out_stride) {
+  const int dim = t.dim;
+  const long long total = n * dim;
+  for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
+       x += (long long)gridDim.x * blockDim.x) {
+    const long long i = x / dim;
+    const int j = (int)(x - i * dim);
+    float* row = fps_row_t<IdT>(t, ids[i]);
+    const float d = j < delta_stride ? delta[i * (long long)delta_stride + j] : 0.f;
+    const float old = atomicAdd_system(row + j, d);
+    if (j < out_stride) out[i * (long long)out_stride + j] = old + d;
+  }
+}
+
+extern "C" int fps_push_add_fetch(const ShardTable* t, const void* ids, int id_bytes, long long n,
+                                  const float* delta, int delta_stride, float* out, int out_stride,
+                                  int num_sms, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n * t->dim + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (id_bytes == 4)
+    fps_push_add_fetch_kernel<int><<<(int)blocks, 256, 0, stream>>>(*t, (const int*)ids, n, delta, delta_stride, out, out_stride);
+  else
+    fps_push_add_fetch_kernel<long long><<<(int)blocks, 256, 0, stream>>>(*t, (const long long*)ids, n, delta, delta_stride, out, out_stride);
+  return (int)cudaGetLastError();
+}

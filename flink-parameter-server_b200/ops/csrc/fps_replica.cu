@@ -98,6 +98,10 @@ struct ExchArgs {
   int chunk_rows;           // rows per pipeline stage (chunk_rows * stride/4 <= EX_CHUNK_VEC)
   int sequential;           // 0: interleave destinations chunk by chunk (spreads the NVLink load),
                             // 1: destination after destination (follows the L2-blocked training sweep)
+  int slices;               // > 1: every flush of destination o moves ONE of `slices` equal sub-ranges of
+  int slice_offset;         //   its segment, rotating: slice = (flushes[o] + o + slice_offset) % slices
+  unsigned int skip_mask;   // destinations never exchanged (the worker's own shard is trained in place)
+  int pad_;
 };
 
 __device__ __forceinline__ int ex_nth_set_bit(unsigned mask, int n) {
@@ -119,10 +123,15 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
 
   unsigned mask = a.state != nullptr ? a.state->mask : a.mask_override;
   mask &= (a.master.num_shards >= 32) ? 0xffffffffu : ((1u << a.master.num_shards) - 1u);
+  mask &= ~a.skip_mask;
   const int n_dest = __popc(mask);
   if (n_dest == 0) return;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool sliced = a.slices > 1 && a.state != nullptr;
+  const long long seg_slots = a.slot_hi - a.slot_lo;
+  const long long slice_len = sliced ? (seg_slots + a.slices - 1) / a.slices : seg_slots;
+  __shared__ long long seg_lo[FPS_MAX_SHARDS], seg_hi[FPS_MAX_SHARDS];
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
@@ -130,10 +139,23 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
     }
     mbar_fence_init();
   }
+  if (threadIdx.x < a.master.num_shards) {
+    const int o = threadIdx.x;
+    long long lo = a.slot_lo, hi = a.slot_hi;
+    if (sliced) {   // the rotating sub-range of this destination (flushes[o] was bumped by the policy kernel)
+      const long long sl = (long long)((a.state->flushes[o] + (unsigned long long)(o + a.slice_offset)) %
+                                       (unsigned long long)a.slices);
+      lo = a.slot_lo + sl * slice_len;
+      hi = lo + slice_len < a.slot_hi ? lo + slice_len : a.slot_hi;
+      if (lo > hi) lo = hi;
+    }
+    seg_lo[o] = lo;
+    seg_hi[o] = hi;
+  }
   __syncthreads();
 
-  const long long n_slots = a.slot_hi - a.slot_lo;
-  const long long cps = (n_slots + a.chunk_rows - 1) / a.chunk_rows;   // chunks per segment
+  const long long n_slots = slice_len;
+  const long long cps = (n_slots + a.chunk_rows - 1) / a.chunk_rows;   // chunks per (sub-)segment
   const long long total = cps * n_dest;
 
   // chunk g -> (destination o, first slot, rows)
@@ -148,9 +170,10 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
       di = (int)(g - ci * n_dest);
     }
     o = ex_nth_set_bit(mask, di);
-    slot0 = a.slot_lo + ci * a.chunk_rows;
-    const long long left = a.slot_hi - slot0;
+    slot0 = seg_lo[o] + ci * a.chunk_rows;
+    const long long left = seg_hi[o] - slot0;
     rows = (int)(left < a.chunk_rows ? left : a.chunk_rows);
+    if (rows < 0) rows = 0;
   };
 
   if (warp == 0) {
@@ -167,10 +190,12 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
       const uint32_t bytes = (uint32_t)rows * row_bytes;
       const size_t seg_off = ((size_t)o * (size_t)a.rps + (size_t)slot0) * (size_t)stride;
       float4* st = buf + (size_t)s * 3 * EX_CHUNK_VEC;
-      mbar_arrive_expect_tx(&full[s], 3u * bytes);
-      tma_bulk_g2s(st, a.master.base[o] + (size_t)slot0 * (size_t)stride, bytes, &full[s]);  // NVLink leg
-      tma_bulk_g2s(st + EX_CHUNK_VEC, a.cache + seg_off, bytes, &full[s]);
-      tma_bulk_g2s(st + 2 * EX_CHUNK_VEC, a.base + seg_off, bytes, &full[s]);
+      mbar_arrive_expect_tx(&full[s], 3u * bytes);     // rows == 0 (tail of a short slice): plain arrive
+      if (bytes != 0) {
+        tma_bulk_g2s(st, a.master.base[o] + (size_t)slot0 * (size_t)stride, bytes, &full[s]);  // NVLink leg
+        tma_bulk_g2s(st + EX_CHUNK_VEC, a.cache + seg_off, bytes, &full[s]);
+        tma_bulk_g2s(st + 2 * EX_CHUNK_VEC, a.base + seg_off, bytes, &full[s]);
+      }
     }
     return;
   }
@@ -223,7 +248,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1)
 // Fallback for rows wider than one pipeline stage (> 8 KiB): register-staged loads, same math.
 __global__ void __launch_bounds__(256)
     fps_replica_exchange_wide_kernel(const __grid_constant__ ExchArgs a) {
-  unsigned mask = a.state != nullptr ? a.state->mask : a.mask_override;
+  unsigned mask = (a.state != nullptr ? a.state->mask : a.mask_override) & ~a.skip_mask;
   const int stride = a.master.stride;
   const int nvec = stride >> 2;
   const long long n_slots = a.slot_hi - a.slot_lo;

@@ -410,13 +410,21 @@ def pack_ratings(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
 
 
 def pull_gather(tab: ShardTableC, ids: torch.Tensor, out: torch.Tensor, touch: bool = False,
-                max_inflight_rows: int = 0) -> None:
+                max_inflight_rows: int = 0, credits: Optional[torch.Tensor] = None) -> None:
+    """``out[i] = table[ids[i]]`` (one-sided gather, K1).  Pull limiter: ``credits`` (int32 ``[2]``
+    device tensor, ``credits[0]`` = pullLimit) is the device-side credit counter -- a lane-group takes a
+    credit before it touches the owner and returns it when the answer is stored; ``credits[1]`` counts
+    stalls.  Without it ``max_inflight_rows`` caps the grid (static limiter)."""
     _req(ids, "ids"); _req(out, "out", torch.float32)
     assert out.shape[0] == ids.numel() and out.shape[1] <= tab.stride
+    if credits is not None:
+        _req(credits, "credits", torch.int32)
     _check(lib().fps_pull_gather(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
                                  C.c_longlong(ids.numel()), C.c_void_p(out.data_ptr()),
                                  int(out.shape[1]), int(bool(touch)), sm_count(ids.device.index),
-                                 int(max_inflight_rows), _stream()), "pull_gather")
+                                 int(max_inflight_rows),
+                                 C.c_void_p(credits.data_ptr() if credits is not None else None),
+                                 _stream()), "pull_gather")
     _bump()
 
 
@@ -441,6 +449,20 @@ def push_assign(tab: ShardTableC, ids: torch.Tensor, values: torch.Tensor, touch
                                  int(values.shape[1]), int(bool(touch)), sm_count(ids.device.index),
                                  _stream()), "push_assign")
     _bump()
+
+
+def push_add_fetch(tab: ShardTableC, ids: torch.Tensor, delta: torch.Tensor) -> torch.Tensor:
+    """table[ids[i]] += delta[i] and return the value AFTER each update (the ``(id, newValue)`` PS output
+    of SimplePSLogic.scala:16-25); returning atomics, one per element."""
+    _req(ids, "ids"); _req(delta, "delta", torch.float32)
+    assert delta.shape[0] == ids.numel() and delta.shape[1] <= tab.stride
+    out = torch.empty((ids.numel(), tab.dim), dtype=torch.float32, device=ids.device)
+    _check(lib().fps_push_add_fetch(C.byref(tab), C.c_void_p(ids.data_ptr()), _id_bytes(ids),
+                                    C.c_longlong(ids.numel()), C.c_void_p(delta.data_ptr()),
+                                    int(delta.shape[1]), C.c_void_p(out.data_ptr()), int(out.shape[1]),
+                                    sm_count(ids.device.index), _stream()), "push_add_fetch")
+    _bump()
+    return out
 
 
 def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
@@ -486,13 +508,15 @@ class ExchArgsC(C.Structure):
     _fields_ = [("master", ShardTableC), ("cache", C.c_void_p), ("base", C.c_void_p),
                 ("rps", C.c_longlong), ("slot_lo", C.c_longlong), ("slot_hi", C.c_longlong),
                 ("state", C.c_void_p), ("mask_override", C.c_uint), ("n_stages", C.c_int),
-                ("chunk_rows", C.c_int), ("sequential", C.c_int)]
+                ("chunk_rows", C.c_int), ("sequential", C.c_int), ("slices", C.c_int),
+                ("slice_offset", C.c_int), ("skip_mask", C.c_uint), ("pad_", C.c_int)]
 
 
 def replica_exchange(master: ShardTableC, cache: torch.Tensor, base: torch.Tensor, *,
                      state: Optional[torch.Tensor] = None, mask: int = 0, n_ctas: int = 32,
                      n_stages: int = 4, slot_lo: int = 0, slot_hi: Optional[int] = None,
-                     sequential: bool = False) -> None:
+                     sequential: bool = False, slices: int = 1, slice_offset: int = 0,
+                     skip_mask: int = 0) -> None:
     """One delta exchange between an owner-major replica and its master shards for the destinations
     flagged in ``state`` (written by :func:`flush_policy`) or in ``mask``: push ``replica - base``
     (REDG over NVLink), fold ``master - base`` into the replica, ``base <- master + pushed delta``.
@@ -509,20 +533,22 @@ def replica_exchange(master: ShardTableC, cache: torch.Tensor, base: torch.Tenso
         a.state = state.data_ptr()
     a.mask_override = int(mask) & 0xFFFFFFFF
     a.n_stages = int(n_stages); a.sequential = int(bool(sequential))
+    a.slices = max(1, int(slices)); a.slice_offset = int(slice_offset); a.skip_mask = int(skip_mask) & 0xFFFFFFFF
     _check(lib().fps_replica_exchange(C.byref(a), int(n_ctas), _stream()), "replica_exchange")
     _bump()
 
 
-def segment_table(t: torch.Tensor, master: ShardTableC) -> ShardTableC:
+def segment_table(t: torch.Tensor, master: ShardTableC, alias: Optional[int] = None) -> ShardTableC:
     """ShardTable over a LOCAL owner-major ``[num_shards * rps, stride]`` tensor: the same
-    ``id -> (owner, slot)`` map as ``master``, every "shard" in local HBM (a worker replica)."""
+    ``id -> (owner, slot)`` map as ``master``, every "shard" in local HBM (a worker replica).
+    ``alias=o``: segment ``o`` is the master shard itself (the worker's own shard is trained in place)."""
     _req(t, "table", torch.float32)
     n = int(master.num_shards)
     rps = int(master.rows_per_shard)
     assert t.shape[0] == n * rps and t.shape[1] == master.stride
     tc = ShardTableC()
     for o in range(n):
-        tc.base[o] = t.data_ptr() + o * rps * t.shape[1] * 4
+        tc.base[o] = master.base[o] if o == alias else t.data_ptr() + o * rps * t.shape[1] * 4
     tc.rows_per_shard = rps; tc.div = master.div; tc.num_shards = n
     tc.dim = master.dim; tc.stride = master.stride; tc.mode = master.mode
     tc.shard_shift = master.shard_shift

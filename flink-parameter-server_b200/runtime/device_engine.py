@@ -51,6 +51,65 @@ class DeviceParameterServerClient(BatchedParameterServerClient):
         self.outputs.append(Left(out))
 
 
+def transform_batched(batches: Iterable[Any], workerLogic: BatchedWorkerLogic, paramInit="zeros",
+                      paramUpdate="add", workerParallelism: int = 1, psParallelism: int = 1,
+                      iterationWaitTime: float = 0, *, num_ids: int, dim: int, pull_limit: int = 0,
+                      paramPartitioner=None, partition: str = "hash", seed: int = 0,
+                      dump_model: bool = True, table: ShardedTable = None, model=None) -> ResultStream:
+    """``transform(batches, BatchedWorkerLogic, paramInit, paramUpdate, workerParallelism,
+    psParallelism, ..., backend="device")`` -- the front door of the tensor tier (FPS:64-80 shape).
+
+    ``paramInit``: ``"zeros"``, a float constant, or ``("uniform", lo, hi)`` (Philox by id);
+    ``paramUpdate``: ``"add"`` (the additive update fused into the push).  ``psParallelism`` shards:
+    one per rank in a multi-process job (``psParallelism <= world``), otherwise ``psParallelism``
+    logical shards on this process's GPUs (:class:`MultiShardTable`); ``paramPartitioner(id) -> shard``
+    (any function) becomes a device ``(owner, slot)`` lookup table.  ``workerParallelism`` worker
+    loops run on their own CUDA streams (per process: ``ceil(wP / world)``)."""
+    import torch.distributed as dist
+
+    if paramUpdate not in ("add", "sum"):
+        raise ValueError('the tensor tier fuses an additive paramUpdate into the push: paramUpdate="add"')
+    if isinstance(paramInit, tuple) and paramInit and paramInit[0] == "uniform":
+        init, rng, const = "uniform", (float(paramInit[1]), float(paramInit[2])), None
+    elif paramInit == "zeros" or paramInit == 0:
+        init, rng, const = "zeros", (0.0, 0.0), None
+    elif isinstance(paramInit, (int, float)):
+        init, rng, const = "zeros", (0.0, 0.0), float(paramInit)
+    else:
+        raise ValueError('paramInit must be "zeros", a constant or ("uniform", lo, hi) on the tensor tier')
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    own = table is None
+    if own:
+        if world > 1:
+            if paramPartitioner is not None:
+                raise NotImplementedError("custom partitioners need one LUT copy per process: single-process only")
+            table = ShardedTable(num_ids, dim, partition=partition, init=init, init_range=rng, seed=seed,
+                                 track_touched=True, num_shards=psParallelism)
+        else:
+            from ..store.multi_shard import MultiShardTable
+
+            table = MultiShardTable(num_ids, dim, psParallelism, partition=partition,
+                                    partitioner=paramPartitioner, init=init, init_range=rng, seed=seed,
+                                    track_touched=True)
+        if const is not None:
+            for t in getattr(table, "shards", [table.local] if table.owns_shard else []):
+                t[:, :dim] = const
+            table.barrier()
+    if model is not None:        # transformWithModelLoad: every entry reaches its shard before training
+        entries = list(model.collect() if hasattr(model, "collect") else model)
+        if entries:
+            dev = table.cuda_device
+            ids = torch.tensor([int(k) for k, _ in entries], dtype=torch.int64, device=dev)
+            vals = torch.stack([torch.as_tensor(v, dtype=torch.float32).reshape(-1) for _, v in entries]).to(dev)
+            table.load(ids, vals)
+        table.barrier()
+    streams = -(-int(workerParallelism) // world)
+    out = transform_device(batches, workerLogic, table, pull_limit=pull_limit, worker_streams=streams,
+                           dump_model=dump_model)
+    out.table = table
+    return out
+
+
 def transform_device(batches: Iterable[Any], workerLogic: BatchedWorkerLogic, table: ShardedTable,
                      pull_limit: int = 0, worker_streams: int = 1, dump_model: bool = True) -> ResultStream:
     dev = table.cuda_device

@@ -133,7 +133,8 @@ class MessagingPS(ParameterServer):
 
 class LocalEngine:
     def __init__(self, workerParallelism: int, psParallelism: int, iterationWaitTime: float,
-                 call_worker_open: bool = True):
+                 call_worker_open: bool = True, ps_batch: int = 4096):
+        self.ps_batch = max(1, int(ps_batch))
         self.wP = int(workerParallelism)
         self.psP = int(psParallelism)
         self.wait_s = max(0.0, float(iterationWaitTime) / 1000.0)
@@ -222,16 +223,34 @@ class LocalEngine:
             def on_push(id, delta) -> None:
                 logic.onPushRecv(id, delta, server)
 
+            # device-resident stores (server/device_logics.py) record requests and execute them in
+            # batches: drain whatever has queued up, decode it, then one flush() = a few kernels
+            inbox = ps_inbox[j]
             try:
                 logic.open({}, RuntimeContext(j, self.psP))
-                while True:
+                flush = getattr(logic, "flush", None)
+                stop = False
+                while not stop:
                     kind, payload = inbox_get()
                     if kind == _STOP:
                         break
+                    n = 1
                     try:
                         on_msg(payload, on_pull, on_push)
+                        if flush is not None:
+                            while n < self.ps_batch:
+                                try:
+                                    kind, payload = inbox.get_nowait()
+                                except queue.Empty:
+                                    break
+                                if kind == _STOP:
+                                    stop = True
+                                    break
+                                n += 1
+                                on_msg(payload, on_pull, on_push)
+                            flush(server)
                     finally:
-                        done()
+                        done(n)
             except BaseException as e:  # noqa: BLE001
                 fail(e)
 

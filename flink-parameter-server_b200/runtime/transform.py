@@ -63,6 +63,27 @@ def default_worker_partitioner(workerParallelism: int) -> Callable[[Any], int]:
 # ------------------------------------------------------------------------------------------
 # the fully general engine call (C5 / C6)
 # ------------------------------------------------------------------------------------------
+def device_ps_logic(psLogic, backend: str):
+    """``backend="device"``: swap a built-in host store for its device-resident twin
+    (server/device_logics.py).  User-defined server logics are arbitrary Python and stay on the host."""
+    if backend in (None, "local", "host"):
+        return psLogic
+    if backend != "device":
+        raise ValueError(f"unknown backend {backend!r} (local | device)")
+    from ..server.device_logics import to_device_logic
+
+    inner = psLogic
+    dev = to_device_logic(inner)
+    if dev is None:
+        import warnings
+
+        warnings.warn(f"{type(psLogic).__name__} is user-defined server code: it runs on the host tier; "
+                      "only the built-in stores (Simple / Loose / Range / Lock) are device-resident",
+                      RuntimeWarning, stacklevel=3)
+        return psLogic
+    return dev
+
+
 def transform_general(trainingData, workerLogic: LooseWorkerLogic,
                       psLogic: LooseParameterServerLogic,
                       paramPartitioner: Callable[[Any], int], wInPartition: Callable[[Any], int],
@@ -85,6 +106,15 @@ def transform(trainingData, workerLogic, *args, **kw) -> ResultStream:
     names_logic = ["psLogic", "workerParallelism", "psParallelism", "iterationWaitTime"]
     names_fn = ["paramInit", "paramUpdate", "workerParallelism", "psParallelism",
                 "iterationWaitTime"]
+    backend = kw.pop("backend", "local")
+    from ..api import BatchedWorkerLogic
+
+    if isinstance(workerLogic, BatchedWorkerLogic):
+        if backend != "device":
+            raise ValueError('a BatchedWorkerLogic runs on the device tensor tier: pass backend="device"')
+        from .device_engine import transform_batched
+
+        return transform_batched(trainingData, workerLogic, *args, **kw)
     first = args[0] if args else None
     if isinstance(first, LooseParameterServerLogic) or "psLogic" in kw:
         second = args[1] if len(args) > 1 else None
@@ -108,6 +138,7 @@ def transform(trainingData, workerLogic, *args, **kw) -> ResultStream:
         psLogic = cls(params["paramInit"], params["paramUpdate"])
     else:
         psLogic = params["psLogic"]
+    psLogic = device_ps_logic(psLogic, backend)
     return transform_general(
         trainingData, workerLogic, psLogic,
         params.get("paramPartitioner") or default_param_partitioner(psP),
@@ -121,10 +152,11 @@ def transform(trainingData, workerLogic, *args, **kw) -> ResultStream:
 
 
 def transformLoose(trainingData, workerLogic, paramInit, paramUpdate, workerParallelism,
-                   psParallelism, iterationWaitTime=DEFAULT_ITERATION_WAIT_TIME) -> ResultStream:
+                   psParallelism, iterationWaitTime=DEFAULT_ITERATION_WAIT_TIME,
+                   backend: str = "local") -> ResultStream:
     """C2: ``PullP != PushP`` with ``LooseSimplePSLogic`` (FPS:122-139)."""
     return transform(trainingData, workerLogic, LooseSimplePSLogic(paramInit, paramUpdate),
-                     workerParallelism, psParallelism, iterationWaitTime)
+                     workerParallelism, psParallelism, iterationWaitTime, backend=backend)
 
 
 # ------------------------------------------------------------------------------------------
@@ -224,6 +256,8 @@ class _LoadingPSLogic(LooseParameterServerLogic):
 
     def open(self, parameters, runtimeContext):
         self.inner.open(parameters, runtimeContext)
+        if hasattr(self.inner, "flush"):          # device-resident inner store: batched execution
+            self.flush = self.inner.flush
 
     def close(self, ps):
         self.inner.close(ps)
@@ -274,8 +308,19 @@ def transformWithModelLoad(model):
 
     def run(trainingData, workerLogic, psLogic, paramPartitioner=None, wInPartition=None,
             workerParallelism=1, psParallelism=1,
-            iterationWaitTime=DEFAULT_ITERATION_WAIT_TIME) -> ResultStream:
+            iterationWaitTime=DEFAULT_ITERATION_WAIT_TIME, backend: str = "local") -> ResultStream:
         wP, psP = int(workerParallelism), int(psParallelism)
+        from ..api import BatchedWorkerLogic
+
+        if isinstance(workerLogic, BatchedWorkerLogic):
+            # tensor tier: psLogic = (paramInit, paramUpdate, {num_ids, dim, ...}); the model is loaded
+            # into the shards with one-sided stores before the first micro-batch
+            from .device_engine import transform_batched
+
+            init, update, opts = psLogic
+            return transform_batched(trainingData, workerLogic, init, update, wP, psP, iterationWaitTime,
+                                     model=model, paramPartitioner=paramPartitioner, **opts)
+        psLogic = device_ps_logic(psLogic, backend)
         user_part = paramPartitioner or default_param_partitioner(psP)
         stream = _prepare_load(model, trainingData, lambda kv: _ModelParam(kv[0], kv[1]))
         return transform_general(
@@ -294,8 +339,10 @@ def transformWithDoubleModelLoad(model):
     def run(trainingData, workerLogic, psLogic, paramPartitioner=None, wInPartition=None,
             workerParallelism=1, psParallelism=1,
             iterationWaitTime=DEFAULT_ITERATION_WAIT_TIME,
-            workerModelPartitioner: Optional[Callable[[Any, int], int]] = None) -> ResultStream:
+            workerModelPartitioner: Optional[Callable[[Any, int], int]] = None,
+            backend: str = "local") -> ResultStream:
         wP, psP = int(workerParallelism), int(psParallelism)
+        psLogic = device_ps_logic(psLogic, backend)
         user_part = paramPartitioner or default_param_partitioner(psP)
 
         def wrap(e):

@@ -38,7 +38,7 @@ class ReplicaCache:
     def __init__(self, table: ShardedTable, sync_every: int = 4, sync_interval_ms: Optional[float] = None,
                  require: str = "any", flush_count: Optional[int] = None,
                  exchange_ctas: Optional[int] = None, stages: Optional[int] = None,
-                 stagger: bool = True, max_outstanding: int = 2):
+                 stagger: bool = True, max_outstanding: int = 2, own_inplace: Optional[bool] = None):
         """Flush trigger = the reference's combinable conditions: ``flush_count`` messages buffered for
         a destination (CountLogic; default: what ``sync_every`` micro-batches send to one destination),
         ``sync_interval_ms`` since the destination's last flush (TimerLogic, device ``globaltimer``),
@@ -51,6 +51,12 @@ class ReplicaCache:
         self.interval_ns = 0 if sync_interval_ms is None else int(float(sync_interval_ms) * 1e6)
         self.require_all = require == "all"
         self.stagger = bool(stagger)
+        # sync_every mode (no explicit count / timer): every micro-batch flushes ONE of `sync_every`
+        # rotating slices of every destination buffer -- uniform NVLink / HBM load per step, a row is
+        # exchanged once per `sync_every` micro-batches, ranks are staggered so that a peer's delta is
+        # seen after ~sync_every/2 steps on average.  An explicit flush_count / sync_interval_ms flushes
+        # whole destination buffers when the device-side policy fires.
+        self.sliced = flush_count is None and sync_interval_ms is None and self.sync_every > 1
         self.n_ctas = int(os.environ.get("FPS_EXCHANGE_CTAS", 32 if exchange_ctas is None else exchange_ctas))
         self.stages = int(os.environ.get("FPS_EXCHANGE_STAGES", 4 if stages is None else stages))
         self.sequential = os.environ.get("FPS_EXCHANGE_SEQUENTIAL", "0") == "1"
@@ -64,10 +70,17 @@ class ReplicaCache:
             # segment o, slot s  <-  master row of the id that lives at (owner o, slot s)
             native.pull_gather(table.table_c, self._segment_ids(), self.cache)
             self.base = self.cache.clone()
-            self.table_c = native.segment_table(self.cache, table.table_c)
+            # the worker's own shard is trained in place (no replica of it, nothing to exchange)
+            if own_inplace is None:
+                own_inplace = os.environ.get("FPS_REPLICA_OWN_INPLACE", "1") == "1"
+            self.own = table.rank if (table.owns_shard and own_inplace) else None
+            self.skip_mask = 0 if self.own is None else (1 << self.own)
+            self.table_c = native.segment_table(self.cache, table.table_c, alias=self.own)
             self.state = torch.zeros(native.FLUSH_STATE_WORDS, dtype=torch.int64, device=dev)
             self.stream = torch.cuda.Stream(device=dev, priority=-1)
         self._pending_events: List[torch.cuda.Event] = []
+        self._timing = os.environ.get("FPS_EXCHANGE_TIMING", "0") == "1"
+        self._timed: List[tuple] = []
         self._armed = False
         self._since_flush = 0
         self.steps = 0
@@ -93,8 +106,16 @@ class ReplicaCache:
         return owner * self.rps + (ids - owner * self.table.div)
 
     def rows(self, ids: torch.Tensor) -> torch.Tensor:
-        """Current replica values of ``ids`` (tests / debugging)."""
-        return self.cache[self.row_index(ids), : self.table.dim]
+        """Current replica values of ``ids`` (tests / debugging); ids of the worker's own shard are read
+        from the master, which is what the training kernels use for them."""
+        idx = self.row_index(ids)
+        out = self.cache[idx, : self.table.dim]
+        if self.own is not None:
+            mine = (idx // self.rps) == self.own
+            if bool(mine.any()):
+                out = out.clone()
+                out[mine] = self.table.local[idx[mine] - self.own * self.rps, : self.table.dim]
+        return out
 
     @property
     def pending(self) -> torch.Tensor:
@@ -104,13 +125,18 @@ class ReplicaCache:
 
     def reserve_total(self) -> int:
         """CTA slots the training kernel must leave free for the exchange running next to it."""
-        return self.n_ctas
+        everything_in_place = self.skip_mask == (1 << self.world) - 1
+        return 0 if everything_in_place else self.n_ctas
 
     # -- policy ---------------------------------------------------------------------------------
     def _arm(self, n_records: int) -> None:
         """First micro-batch: derive the count threshold from the batch size and stagger the
         destinations ((o - rank) % sync_every micro-batches of head start)."""
         per_dest = max(1, int(n_records) // self.world)
+        if self.sliced:
+            self.flush_count = max(1, per_dest // 2)      # fires for every destination after every step
+            self._armed = True
+            return
         if self.flush_count is None:
             self.flush_count = max(1, int((self.sync_every - 0.5) * per_dest))
         if self.stagger and self.sync_every > 1:
@@ -133,10 +159,16 @@ class ReplicaCache:
             native.flush_policy(self.state, self.world, count_max=self.flush_count,
                                 interval_ns=self.interval_ns, require_all=self.require_all,
                                 add_uniform=0 if fed else max(1, int(n_records) // self.world))
+            if self._timing:
+                t0 = torch.cuda.Event(enable_timing=True); t0.record(self.stream)
             native.replica_exchange(self.table.table_c, self.cache, self.base, state=self.state,
-                                    n_ctas=self.n_ctas, n_stages=self.stages, sequential=self.sequential)
-            done = torch.cuda.Event()
+                                    n_ctas=self.n_ctas, n_stages=self.stages, sequential=self.sequential,
+                                    slices=self.sync_every if self.sliced else 1,
+                                    slice_offset=self.rank if self.stagger else 0, skip_mask=self.skip_mask)
+            done = torch.cuda.Event(enable_timing=self._timing)
             done.record(self.stream)
+            if self._timing:
+                self._timed.append((t0, done))
         self._pending_events.append(done)
         if len(self._pending_events) > self.max_outstanding:   # bounded staleness / run-ahead
             cur.wait_event(self._pending_events.pop(0))
@@ -155,7 +187,7 @@ class ReplicaCache:
             native.flush_policy(self.state, self.world, force=True)
             n = 2 * native.sm_count(self.table.device) if wide else self.n_ctas
             native.replica_exchange(self.table.table_c, self.cache, self.base, state=self.state,
-                                    n_ctas=n, n_stages=self.stages)
+                                    n_ctas=n, n_stages=self.stages, skip_mask=self.skip_mask)
             done = torch.cuda.Event()
             done.record(self.stream)
         self._pending_events.append(done)
@@ -180,6 +212,14 @@ class ReplicaCache:
         self._since_flush = 1
         self.flush()
         self.table.barrier()
+
+    def timing_summary(self):
+        """``FPS_EXCHANGE_TIMING=1``: device time of the per-step exchange kernels (ms)."""
+        if not self._timed:
+            return None
+        torch.cuda.synchronize(self.table.device)
+        ms = sorted(a.elapsed_time(b) for a, b in self._timed)
+        return {"n": len(ms), "median_ms": ms[len(ms) // 2], "p90_ms": ms[int(len(ms) * 0.9)], "max_ms": ms[-1]}
 
     def flush_counts(self) -> List[int]:
         """Number of flushes per destination so far (device counters)."""

@@ -141,10 +141,26 @@ class ShardedTable:
         self._reject_negative(ids)
         if out is None:
             out = torch.empty((ids.numel(), self.dim), dtype=torch.float32, device=ids.device)
-        native.pull_gather(self.table_c, ids, out, touch=self.track_touched,
-                           max_inflight_rows=pull_limit)
+        native.pull_gather(self._table_on(ids.device), ids, out, touch=self.track_touched,
+                           credits=self._credits(pull_limit, ids.device) if pull_limit > 0 else None)
         METRICS.inc("ps_pull_rows", ids.numel())
         return out
+
+    def _table_on(self, device) -> native.ShardTableC:
+        """The pointer table valid on ``device`` (MultiShardTable keeps one LUT copy per GPU)."""
+        tf = getattr(self, "table_for", None)
+        return tf(device.index) if tf is not None and device.index is not None else self.table_c
+
+    def _credits(self, pull_limit: int, device) -> torch.Tensor:
+        """Device credit counter of the pull limiter: ``[credits, stalls]``, armed with ``pull_limit``."""
+        key = (int(pull_limit), str(device))
+        store = self.__dict__.setdefault("_credit_counters", {})
+        if key not in store:
+            store[key] = torch.tensor([int(pull_limit), 0], dtype=torch.int32, device=device)
+        return store[key]
+
+    def credit_stalls(self) -> int:
+        return sum(int(c[1]) for c in self.__dict__.get("_credit_counters", {}).values())
 
     def _reject_negative(self, ids: torch.Tensor) -> None:
         """``FPS_VALIDATE_IDS=1``: range-check ids (one host sync per call).  The device tables address
@@ -155,13 +171,13 @@ class ShardedTable:
     def push(self, ids: torch.Tensor, deltas: torch.Tensor, scale: float = 1.0) -> None:
         """table[ids[i]] += scale * deltas[i] -- push fused with the additive paramUpdate (K2)."""
         self._reject_negative(ids)
-        native.push_add(self.table_c, ids, deltas, scale=scale, touch=self.track_touched,
-                        nan_flag=self.nan_flag)
+        native.push_add(self._table_on(ids.device), ids, deltas, scale=scale, touch=self.track_touched,
+                        nan_flag=self.nan_flag if self.nan_flag.device == ids.device else None)
         METRICS.inc("ps_push_rows", ids.numel())
 
     def pull_dot(self, ids: torch.Tensor, local_vectors: torch.Tensor) -> torch.Tensor:
         score = torch.empty(ids.numel(), dtype=torch.float32, device=ids.device)
-        native.pull_dot(self.table_c, ids, local_vectors, score)
+        native.pull_dot(self._table_on(ids.device), ids, local_vectors, score)
         return score
 
     def check_finite(self) -> None:
@@ -190,7 +206,7 @@ class ShardedTable:
 
     def load(self, ids: torch.Tensor, values: torch.Tensor) -> None:
         """Model load: overwrite rows with given values (any rank may load any id)."""
-        native.push_assign(self.table_c, ids, values.to(torch.float32).contiguous(),
+        native.push_assign(self._table_on(ids.device), ids, values.to(torch.float32).contiguous(),
                            touch=self.track_touched)
 
     def barrier(self) -> None:

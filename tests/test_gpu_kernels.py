@@ -286,7 +286,7 @@ def test_item_cache_mode_single_gpu_matches_direct_mode(dev):
     nu, ni, k, b = 6000, 5000, 64, 3000
     m_direct = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, item_cache=False)
     m_cache = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, item_cache=True,
-                             sync_every=2)
+                             sync_every=2, replica_own_inplace=False)
     V0 = m_cache.items.local.clone()
     rep = m_cache.replica
     assert torch.equal(rep.cache[:ni], V0[:ni]) and torch.equal(rep.base, rep.cache)
@@ -390,16 +390,16 @@ def test_replica_flush_policy_count_timer_any_all_on_device(dev):
     from fps_b200.store.sharded_table import ShardedTable
 
     t = ShardedTable(500, 16, seed=1)
-    rc = ReplicaCache(t, flush_count=300, stagger=False)       # count only: 100 messages per step
+    rc = ReplicaCache(t, flush_count=300, stagger=False, own_inplace=False)       # count only: 100 messages per step
     for _ in range(7):
         rc.after_step(100)
     torch.cuda.synchronize()
     assert rc.flush_counts() == [2]                             # fired at 300 and 600 messages
     assert int(rc.pending[0]) == 100                            # 700 - 2 * 300
-    rc = ReplicaCache(t, flush_count=10 ** 9, sync_interval_ms=20, stagger=False)   # timer only
+    rc = ReplicaCache(t, flush_count=10 ** 9, sync_interval_ms=20, stagger=False, own_inplace=False)   # timer only
     rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [0]
     time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
-    rc = ReplicaCache(t, flush_count=2, sync_interval_ms=20, require="all", stagger=False)
+    rc = ReplicaCache(t, flush_count=2, sync_interval_ms=20, require="all", stagger=False, own_inplace=False)
     rc.after_step(1); rc.after_step(1); torch.cuda.synchronize()
     assert rc.flush_counts() == [0]                             # count reached, deadline not yet
     time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
@@ -428,7 +428,7 @@ def test_replica_exchange_conserves_every_delta_single_rank(dev, dim, n):
     t = ShardedTable(n, dim, seed=3, init_range=(-1, 1))
     all_ids = torch.arange(n, device=dev)
     init = t.pull(all_ids).clone()
-    rc = ReplicaCache(t, sync_every=2)
+    rc = ReplicaCache(t, sync_every=2, own_inplace=False)
     g = torch.Generator(device="cpu").manual_seed(dim)
     total = torch.zeros(n, dim, device=dev)
     for step in range(9):
