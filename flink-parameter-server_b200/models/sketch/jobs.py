@@ -33,7 +33,7 @@ def _ps_only(result) -> List[Any]:
 
 
 def _device_train(kind: str, src, numHashes: int, arraySize: int = 0, capacity=None, group=None,
-                  chunk: int = 65536) -> List[Any]:
+                  chunk: int = 65536, time_aware: bool = False) -> List[Any]:
     """``backend="device"`` of the push-only train jobs: the same ``(tweetId, [words])`` stream updates a
     :class:`~fps_b200.models.sketch.device.DeviceSketch` (one-sided ``red.or / red.add / red.min`` pushes)
     and the ``close()`` dump has the host jobs' shape.  Integer tweet ids; the hash family is the device
@@ -42,14 +42,45 @@ def _device_train(kind: str, src, numHashes: int, arraySize: int = 0, capacity=N
     feeds its partition of the stream and gets the dump of its own shard."""
     from .device import DeviceSketch
 
-    recs = [(int(r[0]), list(r[1])) for r in (src.collect() if hasattr(src, "collect") else src)]
+    recs = [(int(r[0]), list(r[1])) + ((int(r[2]),) if time_aware else ())
+            for r in (src.collect() if hasattr(src, "collect") else src)]
     if capacity is None:
-        capacity = max(1, len({w for _t, ws in recs for w in ws}))
-    sk = DeviceSketch(kind, int(capacity), numHashes, arraySize, group=group)
+        capacity = max(1, len({(w, r[2]) if time_aware else w for r in recs for w in r[1]}))
+    sk = DeviceSketch(kind, int(capacity), numHashes, arraySize, group=group, time_aware=time_aware)
     try:
         for a in range(0, len(recs), chunk):
             sk.update(recs[a:a + chunk])
         return sk.model()
+    finally:
+        sk.close()
+
+
+def _device_predict(kind: str, queries, model, numHashes: int, K: int, arraySize: int = 0, numMeans: int = 1,
+                    time_aware: bool = False, counts=None, cooccurrence: bool = False, capacity=None,
+                    group=None) -> List[Any]:
+    """``backend="device"`` of the predict jobs: the model dump is loaded into a
+    :class:`~fps_b200.models.sketch.device.DeviceSketch` (one-sided stores), every query word's sketch is
+    pulled and scored against every shard by the scan kernels (popcount / median-of-means / equality
+    count, ops/csrc/fps_sketch.cu), the local top-K lists are gathered by one-sided stores and merged on
+    the device.  Output shape = the host jobs': ``[(queryId | (queryId, slot), [(score, key)] best first)]``."""
+    from .device import DeviceSketch
+
+    entries = list(model.collect() if hasattr(model, "collect") else model)
+    if capacity is None:
+        capacity = max(1, len(entries))
+    sk = DeviceSketch(kind, int(capacity), numHashes, arraySize, group=group, time_aware=time_aware)
+    try:
+        sk.load_model(entries, counts)
+        out = []
+        for q in (queries.collect() if hasattr(queries, "collect") else queries):
+            queryId, word = q if isinstance(q, (tuple, list)) else (java_string_hash(q), q)
+            if time_aware:
+                for slot in sk.slots_of(word):       # one pull -> one answer per time slot of the word
+                    top = sk.query(word, K, num_means=numMeans, slot=slot)
+                    out.append(((queryId, slot), [(sc, key[0]) for sc, key in top]))
+            else:
+                out.append((queryId, sk.query(word, K, num_means=numMeans, cooccurrence=cooccurrence)))
+        return out
     finally:
         sk.close()
 
@@ -166,9 +197,12 @@ def _predict(src, model, workerLogic, serverLogic, K, workerParallelism, psParal
 
 
 def bloomPredict(src, model, arraySize: int, numHashes: int, K: int, workerParallelism: int,
-                 psParallelism: int, pullLimit: int, iterationWaitTime: float = 10000):
+                 psParallelism: int, pullLimit: int, iterationWaitTime: float = 10000,
+                 backend: str = "local", **device_kw):
     """Predict: ``src`` = ``(queryId, word)``, ``model`` = ``(wordHash, bitset)`` pairs ->
     ``[(queryId, [(estimatedCoOccurrence, wordHash)] best-first)]`` (BloomFilterPredict.scala:33-139)."""
+    if backend == "device":
+        return _device_predict("bloom", src, model, numHashes, K, arraySize=arraySize, **device_kw)
     m = as_stream(model).map(lambda kv: (kv[0], Right(kv[1])))
     return _predict(src, m, _BroadcastQueryWorker(psParallelism),
                     BloomPredictPSLogic(arraySize, numHashes, K), K, workerParallelism,
@@ -208,8 +242,10 @@ class _TimeAwareBloomWorker(WorkerLogic):
 
 
 def timeAwareBloomFilter(src, arraySize, numHashes, workerParallelism, psParallelism,
-                         iterationWaitTime=10000):
+                         iterationWaitTime=10000, backend: str = "local", **device_kw):
     """(TimeAwareBloomFilter.scala:31-92) -> ``[((wordHash, slot), bitset)]``."""
+    if backend == "device":
+        return _device_train("bloom", src, numHashes, arraySize, time_aware=True, **device_kw)
     return _ps_only(transform(src, _TimeAwareBloomWorker(arraySize, numHashes), TimeAwareBloomPSLogic(),
                               workerParallelism, psParallelism, iterationWaitTime))
 
@@ -261,9 +297,12 @@ class _TimeAwareBroadcastWorker(WorkerLogic):
 
 
 def timeAwareBloomPredict(src, model, arraySize, numHashes, K, workerParallelism, psParallelism,
-                          pullLimit, iterationWaitTime=10000):
+                          pullLimit, iterationWaitTime=10000, backend: str = "local", **device_kw):
     """``model`` = ``((wordHash, slot), bitset)`` pairs -> ``[((queryId, slot), topK)]``.
     The pull limiter must allow multi-answer pulls, so the limit is applied per query word."""
+    if backend == "device":
+        return _device_predict("bloom", src, model, numHashes, K, arraySize=arraySize, time_aware=True,
+                               **device_kw)
     m = as_stream(model).map(lambda kv: (kv[0][0], Right((kv[0][1], kv[1]))))
     res = transformWithModelLoad(m)(
         src, _TimeAwareBroadcastWorker(psParallelism), TimeAwareBloomPredictPSLogic(arraySize, numHashes, K),
@@ -341,8 +380,11 @@ def tugOfWar(src, numHashes, workerParallelism, psParallelism, iterationWaitTime
                               workerParallelism, psParallelism, iterationWaitTime))
 
 
-def timeAwareTugOfWar(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000):
+def timeAwareTugOfWar(src, numHashes, workerParallelism, psParallelism, iterationWaitTime=10000,
+                      backend: str = "local", **device_kw):
     """(TimeAwareTugOfWar.scala:17-60) -> ``[((wordHash, slot), counters)]``."""
+    if backend == "device":
+        return _device_train("tow", src, numHashes, time_aware=True, **device_kw)
     return _ps_only(transform(src, _ToWWorker(numHashes, True), TimeAwareToWPSLogic(numHashes),
                               workerParallelism, psParallelism, iterationWaitTime))
 
@@ -400,8 +442,10 @@ class SketchPSLogic(ParameterServerLogic):
 
 
 def tugOfWarPredict(src, model, numHashes, numMeans, K, workerParallelism, psParallelism, pullLimit,
-                    iterationWaitTime=10000):
+                    iterationWaitTime=10000, backend: str = "local", **device_kw):
     """(TugOfWarPredict.scala:17-108) ``model`` = ``(wordHash, counters)`` pairs."""
+    if backend == "device":
+        return _device_predict("tow", src, model, numHashes, K, numMeans=numMeans, **device_kw)
     m = as_stream(model).map(lambda kv: (kv[0], Right(kv[1])))
     return _predict(src, m, _BroadcastQueryWorker(psParallelism),
                     SketchPredictPSLogic(numHashes, numMeans, K), K, workerParallelism, psParallelism,
@@ -432,8 +476,11 @@ class TimeAwareToWPredictPSLogic(ParameterServerLogic):
 
 
 def timeAwareTugOfWarPredict(src, model, numHashes, numMeans, K, workerParallelism, psParallelism,
-                             pullLimit, iterationWaitTime=10000):
+                             pullLimit, iterationWaitTime=10000, backend: str = "local", **device_kw):
     """(TimeAwareTugOfWarPredict.scala:20-105) ``model`` = ``((wordHash, slot), counters)``."""
+    if backend == "device":
+        return _device_predict("tow", src, model, numHashes, K, numMeans=numMeans, time_aware=True,
+                               **device_kw)
     m = as_stream(model).map(lambda kv: (kv[0][0], Right((kv[0][1], kv[1]))))
     res = transformWithModelLoad(m)(
         src, _TimeAwareBroadcastWorker(psParallelism), TimeAwareToWPredictPSLogic(numHashes, numMeans, K),
@@ -579,10 +626,14 @@ def word_count(train) -> Dict[int, int]:
 
 
 def minhashPredict(words, train, model, numHashes, K, workerParallelism, psParallelism, pullLimit,
-                   iterationWaitTime=10000):
+                   iterationWaitTime=10000, backend: str = "local", **device_kw):
     """(MinHashPredict.scala:60-141): Jaccard estimates converted to co-occurrence counts with the
     word frequencies of ``train``: ``round(J * (f_q + f_w) / (J + 1))``; per query the list is
     sorted by that count, best first."""
+    if backend == "device":   # Jaccard scan + the Aggregate step (word frequencies) in one kernel
+        res = _device_predict("minhash", list(as_stream(words).collect()), model, numHashes, K,
+                              counts=word_count(train), cooccurrence=True, **device_kw)
+        return [(q, [(key, int(c)) for c, key in lst]) for q, lst in res]
     searchWords = as_stream(words).map(java_string_hash)
     m = as_stream(model).map(lambda kv: (kv[0], Right(kv[1])))
     res = transformWithModelLoad(m)(

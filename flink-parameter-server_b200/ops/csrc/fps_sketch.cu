@@ -80,11 +80,15 @@ extern "C" int fps_sketch_update(const ShardTable* t, int kind, const int* keys,
 __global__ void __launch_bounds__(256)
     fps_bloom_query_kernel(const unsigned int* __restrict__ local_rows, long long n_rows, int stride_words,
                            int n_words, const unsigned int* __restrict__ query, float m, float k,
-                           float* __restrict__ est) {
+                           const int* __restrict__ key_slot, int query_slot, float* __restrict__ est) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp; r < n_rows; r += n_warps) {
+    if (key_slot != nullptr && key_slot[r] != query_slot) {   // time-aware: same-slot keys only
+      if (lane == 0) est[r] = -3.0e38f;
+      continue;
+    }
     const unsigned int* row = local_rows + r * (long long)stride_words;
     int cb = 0, cu = 0, cq = 0;
     for (int w = lane; w < n_words; w += 32) {
@@ -107,12 +111,123 @@ __global__ void __launch_bounds__(256)
 }
 
 extern "C" int fps_bloom_query(const unsigned int* local_rows, long long n_rows, int stride_words,
-                               int n_words, const unsigned int* query, float m, float k, float* est,
+                               int n_words, const unsigned int* query, float m, float k,
+                               const int* key_slot, int query_slot, float* est,
                                int num_sms, cudaStream_t stream) {
   if (n_rows <= 0) return 0;
   long long blocks = (n_rows * 32 + 255) / 256;
   if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
   fps_bloom_query_kernel<<<(int)blocks, 256, 0, stream>>>(local_rows, n_rows, stride_words, n_words,
-                                                          query, m, k, est);
+                                                          query, m, k, key_slot, query_slot, est);
+  return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------
+// K9 query: tug-of-war co-occurrence estimate = MEDIAN over `num_means` groups of the MEAN slice
+// dot-product of the int32 counters (SketchPredictPSLogic.scala:23-40).  One warp per local key;
+// lane g keeps the mean of group g, the median is found by rank counting over shuffles.
+// K10 query: MinHash Jaccard estimate = fraction of signature slots holding the same tweet id
+// (MinHashPredictPSLogic.scala:33-36), optionally converted to a co-occurrence count with the word
+// frequencies, round(J * (f_q + f_w) / (J + 1))  (MinHashPredict.scala:60-141 Aggregate).
+// Time-aware variants (TimeAwareToWPredictPSLogic.scala, TimeAwareBloomPredictPSLogic.scala:19-27): keys
+// are (word, timeSlot); `key_slot[r] != query_slot` rows are excluded from the scan.
+// ----------------------------------------------------------------------------------------
+#define SK_NEG_INF (-3.0e38f)
+
+__global__ void __launch_bounds__(256)
+    fps_tow_query_kernel(const int* __restrict__ rows, long long n_rows, int stride_words, int n_hashes,
+                         int num_means, const int* __restrict__ query, const int* __restrict__ key_slot,
+                         int query_slot, float* __restrict__ est) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int size = max(1, (n_hashes + num_means - 1) / num_means);
+  const int m = (n_hashes + size - 1) / size;   // groups actually formed (<= 32)
+  for (long long r = warp; r < n_rows; r += n_warps) {
+    if (key_slot != nullptr && key_slot[r] != query_slot) {
+      if (lane == 0) est[r] = SK_NEG_INF;
+      continue;
+    }
+    const int* row = rows + r * (long long)stride_words;
+    double mine = 0.0;
+    for (int g = 0; g < m; ++g) {
+      const int lo = g * size, hi = min(n_hashes, lo + size);
+      long long acc = 0;
+      for (int j = lo + lane; j < hi; j += 32) acc += (long long)row[j] * (long long)query[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == g) mine = (double)acc / (double)(hi - lo);
+    }
+    const bool valid = lane < m;
+    int rank = 0;                                   // position in DESCENDING order, ties by lane
+    for (int k = 0; k < m; ++k) {
+      const double vk = __shfl_sync(0xffffffffu, mine, k);
+      if (valid && (vk > mine || (vk == mine && k < lane))) ++rank;
+    }
+    double c = 0.0;
+    if (valid && rank == m / 2) c += mine;
+    if (valid && (m & 1) == 0 && rank == m / 2 - 1) c += mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) est[r] = (float)((m & 1) == 0 ? 0.5 * c : c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    fps_minhash_query_kernel(const unsigned long long* __restrict__ rows, long long n_rows,
+                             int stride_u64, int n_hashes, const unsigned long long* __restrict__ query,
+                             const int* __restrict__ key_slot, int query_slot,
+                             const float* __restrict__ freq, float query_freq, float* __restrict__ est) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += n_warps) {
+    if (key_slot != nullptr && key_slot[r] != query_slot) {
+      if (lane == 0) est[r] = SK_NEG_INF;
+      continue;
+    }
+    const unsigned long long* row = rows + r * (long long)stride_u64;
+    int eq = 0, filled = 0, qfilled = 0;
+    for (int j = lane; j < n_hashes; j += 32) {
+      const unsigned long long a = row[j], b = query[j];
+      filled += a != ~0ull;
+      qfilled += b != ~0ull;
+      eq += (a != ~0ull) && (b != ~0ull) && ((unsigned int)a == (unsigned int)b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      eq += __shfl_xor_sync(0xffffffffu, eq, o);
+      filled += __shfl_xor_sync(0xffffffffu, filled, o);
+      qfilled += __shfl_xor_sync(0xffffffffu, qfilled, o);
+    }
+    if (lane == 0) {
+      float j = (filled != 0 && qfilled != 0) ? (float)eq / (float)n_hashes : 0.f;
+      if (filled == 0) j = SK_NEG_INF;                         // not a key of this shard
+      else if (freq != nullptr) j = rintf(j * (query_freq + freq[r]) / (j + 1.f));
+      est[r] = j;
+    }
+  }
+}
+
+extern "C" int fps_sketch_query(int kind, const void* rows, long long n_rows, int stride_words, int n_hashes,
+                                int num_means, const void* query, const int* key_slot, int query_slot,
+                                const float* freq, float query_freq, float* est, int num_sms,
+                                cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  long long blocks = (n_rows * 32 + 255) / 256;
+  if (blocks > (long long)num_sms * 8) blocks = (long long)num_sms * 8;
+  if (kind == SK_TOW) {
+    if (num_means < 1) num_means = 1;
+    const int size = (n_hashes + num_means - 1) / num_means;
+    if ((n_hashes + size - 1) / size > 32) return -1008;   // more than 32 groups: not supported on the device
+    fps_tow_query_kernel<<<(int)blocks, 256, 0, stream>>>((const int*)rows, n_rows, stride_words, n_hashes,
+                                                          num_means, (const int*)query, key_slot, query_slot, est);
+  } else if (kind == SK_MINHASH) {
+    fps_minhash_query_kernel<<<(int)blocks, 256, 0, stream>>>(
+        (const unsigned long long*)rows, n_rows, stride_words / 2, n_hashes, (const unsigned long long*)query,
+        key_slot, query_slot, freq, query_freq, est);
+  } else {
+    return -1007;
+  }
   return (int)cudaGetLastError();
 }

@@ -749,12 +749,39 @@ def sketch_update(tab: ShardTableC, kind: str, keys: torch.Tensor, tweets: torch
     _bump()
 
 
-def bloom_query(local_rows: torch.Tensor, n_words: int, query: torch.Tensor, m: float, k: float,
-                est: torch.Tensor) -> None:
+def sketch_query(kind: str, local_rows: torch.Tensor, n_words: int, num_hashes: int, query: torch.Tensor,
+                 est: torch.Tensor, num_means: int = 1, key_slot: Optional[torch.Tensor] = None,
+                 query_slot: int = 0, freq: Optional[torch.Tensor] = None, query_freq: float = 0.0) -> None:
+    """Scan the local shard with one warp per key: tug-of-war median-of-means estimate (``kind="tow"``)
+    or MinHash Jaccard / co-occurrence count (``kind="minhash"``, ``freq`` = per-key word frequencies).
+    ``key_slot`` / ``query_slot`` restrict the scan to one time slot (time-aware jobs).  Rows that are not
+    keys score ``-3e38``.  csrc/fps_sketch.cu."""
     _req(local_rows, "local_rows", torch.int32); _req(query, "query", torch.int32)
     _req(est, "est", torch.float32)
+    if key_slot is not None:
+        _req(key_slot, "key_slot", torch.int32)
+    if freq is not None:
+        _req(freq, "freq", torch.float32)
+    _check(lib().fps_sketch_query(SKETCH_KINDS[kind], C.c_void_p(local_rows.data_ptr()),
+                                  C.c_longlong(local_rows.shape[0]), int(local_rows.shape[1]),
+                                  int(num_hashes), int(num_means), C.c_void_p(query.data_ptr()),
+                                  C.c_void_p(key_slot.data_ptr() if key_slot is not None else None),
+                                  int(query_slot), C.c_void_p(freq.data_ptr() if freq is not None else None),
+                                  C.c_float(query_freq), C.c_void_p(est.data_ptr()),
+                                  sm_count(local_rows.device.index), _stream()), "sketch_query")
+    _bump()
+
+
+def bloom_query(local_rows: torch.Tensor, n_words: int, query: torch.Tensor, m: float, k: float,
+                est: torch.Tensor, key_slot: Optional[torch.Tensor] = None, query_slot: int = 0) -> None:
+    _req(local_rows, "local_rows", torch.int32); _req(query, "query", torch.int32)
+    _req(est, "est", torch.float32)
+    if key_slot is not None:
+        _req(key_slot, "key_slot", torch.int32)
     _check(lib().fps_bloom_query(C.c_void_p(local_rows.data_ptr()), C.c_longlong(local_rows.shape[0]),
                                  int(local_rows.shape[1]), int(n_words), C.c_void_p(query.data_ptr()),
-                                 C.c_float(m), C.c_float(k), C.c_void_p(est.data_ptr()),
+                                 C.c_float(m), C.c_float(k),
+                                 C.c_void_p(key_slot.data_ptr() if key_slot is not None else None),
+                                 int(query_slot), C.c_void_p(est.data_ptr()),
                                  sm_count(local_rows.device.index), _stream()), "bloom_query")
     _bump()

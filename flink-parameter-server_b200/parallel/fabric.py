@@ -140,3 +140,80 @@ class SymmetricHeap:
             self._cleanup_ipc()
         except Exception:
             pass
+
+
+class P2PGather:
+    """One-sided gather of small per-rank tensors (partial top-K lists, E9 of SURVEY §2.11;
+    reference: the parallelism-1 merge sinks, CollectTopKFromEachWorker.scala:41-56) -- no NCCL.
+
+    Every rank owns ``world`` receive slots (x 2, alternating by call) in a symmetric heap.  A sender
+    stores its tensor straight into the destination's slot ``[rank]`` through the peer mapping (a copy
+    kernel whose destination is NVLink peer memory) and then stores the call's sequence number into the
+    destination's flag ``[rank]``; the destination polls its own flags, reads its slots and stores an
+    acknowledgement back, which is what lets a sender reuse a slot two calls later.
+    """
+
+    def __init__(self, max_bytes: int, group=None, device: Optional[int] = None):
+        self.slot = int((max_bytes + 255) // 256 * 256)
+        self.group = group
+        self.world = dist.get_world_size(group) if _dist_ready() else 1
+        self.rank = dist.get_rank(group) if _dist_ready() else 0
+        w = self.world
+        self._flags_off = 2 * w * self.slot
+        self._acks_off = self._flags_off + 256 * ((8 * w + 255) // 256)
+        total = self._acks_off + 256 * ((8 * w + 255) // 256)
+        self.heap = SymmetricHeap(total, group=group, device=device)
+        self.device = self.heap.device
+        self.seq = 0
+        self._last_use = [[0, 0] for _ in range(w)]   # per destination and buffer: the call that used it last
+        self.flags = self.heap.local_tensor((w,), torch.int64, self._flags_off)
+        self.acks = self.heap.local_tensor((w,), torch.int64, self._acks_off)
+        self.heap.barrier()
+
+    def _wait(self, t: torch.Tensor, idx, value: int, what: str, timeout_s: float = 60.0) -> None:
+        import time
+
+        t0 = time.time()
+        while True:
+            cur = t if idx is None else t[idx]
+            if int(cur.min().item()) >= value:
+                return
+            if time.time() - t0 > timeout_s:
+                raise TimeoutError(f"P2PGather: {what} did not arrive (rank {self.rank}, seq {value})")
+            time.sleep(0.0002)
+
+    def gather(self, x: torch.Tensor, dst: Optional[int] = 0):
+        """Collective.  ``dst=None``: every rank receives every tensor (all-gather); otherwise only
+        ``dst`` does.  Returns the list of ``world`` tensors (same shape / dtype as ``x``) or ``None``."""
+        x = x.contiguous()
+        nbytes = x.numel() * x.element_size()
+        if nbytes > self.slot:
+            raise ValueError(f"tensor of {nbytes} bytes exceeds the gather slot ({self.slot})")
+        if self.world == 1:
+            return [x.clone()]
+        self.seq += 1
+        seq, buf = self.seq, self.seq & 1
+        dsts = range(self.world) if dst is None else [int(dst)]
+        raw = x.view(torch.uint8).reshape(-1)
+        for d in dsts:
+            prev = self._last_use[d][buf]
+            if prev:      # slot reuse: the destination must have consumed the call that used it last
+                self._wait(self.acks, d, prev, f"ack of rank {d}")
+            self._last_use[d][buf] = seq
+            off = (buf * self.world + self.rank) * self.slot
+            self.heap.peer_tensor(d, (nbytes,), torch.uint8, off).copy_(raw)          # one-sided store
+            self.heap.peer_tensor(d, (1,), torch.int64, self._flags_off + 8 * self.rank).fill_(seq)
+        if dst is not None and self.rank != dst:
+            return None
+        self._wait(self.flags, None, seq, "a partial list")
+        out = []
+        for r in range(self.world):
+            off = (buf * self.world + r) * self.slot
+            out.append(self.heap.local_tensor((nbytes,), torch.uint8, off).clone().view(x.dtype).reshape(x.shape))
+        torch.cuda.current_stream(self.device).synchronize()
+        for r in range(self.world):   # acknowledge: the slots of this call may be overwritten
+            self.heap.peer_tensor(r, (1,), torch.int64, self._acks_off + 8 * self.rank).fill_(seq)
+        return out
+
+    def close(self) -> None:
+        self.heap.close()
