@@ -196,48 +196,117 @@ def ps_topk_generator_device(src, model, K: int = 100, workerK: int = 75, userMe
     return [(item, ts, topk) for (_u, item, ts, topk) in _seen_filter(rows, K, userMemory)]
 
 
+class _LearnerModel:
+    """The model the learner+generator leaves behind: user vectors on the PS table, this rank's item rows."""
+
+    def __init__(self, users, items, world, rank, k):
+        self.users, self.items, self.world, self.rank, self.k = users, items, world, rank, k
+
+    def predict(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+        """u.v for pairs whose ITEM is owned by this rank (user rows are pulled from the PS)."""
+        rows = self.items[(items.to(torch.int64) // self.world)].contiguous()
+        return self.users.pull_dot(users, rows)
+
+    def close(self) -> None:
+        self.users.close()
+
+
 def ps_online_learner_and_generator_device(src, numFactors=10, rangeMin=-0.001, rangeMax=0.001,
                                            learningRate=0.01, negativeSampleRate=0, userMemory=65535,
-                                           K=100, pullLimit=0, seed=0, plain_residual=False,
+                                           K=100, workerK=None, pullLimit=0, seed=0, plain_residual=False,
                                            numUsers: Optional[int] = None, numItems: Optional[int] = None,
                                            batch_size: int = 4096, group=None):
     """Online MF plus a top-K list for every incoming rating, computed BEFORE the model sees that rating
-    (prequential evaluation; capability of ``psOnlineLearnerAndGenerator``,
-    PSOnlineMatrixFactorizationAndTopKGenerator.scala:51-101) on the device tier: per micro-batch
-    (1) score the batch's users against the item table with the tensor-core kernel, (2) train on the
-    batch with the fused kernel.  Prequential at micro-batch granularity (``batch_size``).  Single rank.
-    Returns ``[(userId, itemId, timestamp, [(score, itemId)])]`` and leaves the model in ``.model``."""
+    (prequential evaluation; ``psOnlineLearnerAndGenerator``,
+    PSOnlineMatrixFactorizationAndTopKGenerator.scala:51-101) on the device tier, any number of ranks.
+
+    Roles as in the reference: **user vectors on the parameter server** (a sharded table), **item
+    vectors on the workers** (rank ``item % N`` owns the item).  Every rank is handed the same rating
+    stream (the reference broadcasts each rating to all workers, ``:84-101``).  Per micro-batch:
+
+    1. every rank scores the batch's users -- pulled from the PS by the tcgen05 kernel's A-gather --
+       against ITS item partition (``fps_topk_mma``) and keeps ``workerK`` candidates;
+    2. the partial lists travel to the merge rank as one-sided stores (:class:`P2PGather`) and are
+       merged by ``fps_row_topk`` (``CollectTopKFromEachWorker.scala:41-56``; seen-item filter on the host);
+    3. the OWNER of each rated item trains: its local item row is updated in place and the user delta is
+       pushed to the PS (``...AndTopKGeneratorWorker.scala:128-164``) -- the fused MF kernel with the
+       roles swapped (worker-local rows = items, PS rows = users), negatives drawn from the owner's items.
+
+    Prequential at micro-batch granularity (``batch_size``; 1 reproduces the per-rating order).  The
+    result is a pure function of the stream and the seed, whatever the number of ranks (init is Philox
+    by id).  Rank 0 returns ``[(userId, itemId, timestamp, [(score, itemId)])]`` (other ranks ``[]``);
+    the model is in ``.users`` (the PS table) / ``.items`` (local partition)."""
     import torch.distributed as dist
 
-    from .device_topk import DeviceTopK
+    from ...store.sharded_table import ShardedTable
+    from .device_topk import DeviceTopK, DistributedTopK
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        raise NotImplementedError("the device learner+generator runs on one rank; use DistributedTopK "
-                                  "with DeviceOnlineMF for multi-rank serving")
     recs = list(src.collect() if hasattr(src, "collect") else src)
     if numUsers is None:
-        numUsers = 1 + max(r.user for r in recs)
+        numUsers = 1 + max((r.user for r in recs), default=0)
     if numItems is None:
-        numItems = 1 + max(r.item for r in recs)
-    model = DeviceOnlineMF(numUsers, numItems, numFactors, rangeMin, rangeMax, learningRate,
-                           negativeSampleRate, pull_limit=int(pullLimit or 0),
-                           group=group, seed=seed, err_mode=ERR_PLAIN if plain_residual else ERR_SIGMOID,
-                           item_cache=False, user_memory=min(max(userMemory, 0), 256) if negativeSampleRate else 0)
-    dev = model.cuda_device
+        numItems = 1 + max((r.item for r in recs), default=0)
+    numUsers, numItems = _agree_max(numUsers, numItems, group)
+    ready = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if ready else 1
+    rank = dist.get_rank(group) if ready else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    users = ShardedTable(numUsers, numFactors, group=group, init="uniform", init_range=(rangeMin, rangeMax),
+                         seed=seed * 2 + 2)
+    n_local = -(-numItems // world)
+    items = torch.empty((n_local, users.stride), dtype=torch.float32, device=dev)
+    native.init_rows(items, numFactors, rank, world, native.PART_HASH, n_local, seed * 2 + 1, rangeMin, rangeMax)
+    local_ids = torch.arange(n_local, device=dev, dtype=torch.int64) * world + rank
+    n_valid = int((local_ids < numItems).sum())
+    stats = torch.zeros(2, dtype=torch.float32, device=dev)
+    nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    err_mode = ERR_PLAIN if plain_residual else ERR_SIGMOID
     want = K + (min(userMemory, 4 * K) if userMemory >= 0 else K)
+    wk = max(workerK or 0, want)
+    gen = torch.Generator(device=dev).manual_seed(seed * 7919 + 13)
     rows = []
-    for a in range(0, len(recs), batch_size):
+    users.barrier()
+    # the scorer reads the item partition in place: the fused kernel's updates are seen by the next batch
+    serving = DistributedTopK(users, items[:max(n_valid, 1)], local_ids[:max(n_valid, 1)], group=group)
+    for bno, a in enumerate(range(0, len(recs), batch_size)):
         chunk = recs[a:a + batch_size]
         u = torch.tensor([r.user for r in chunk], dtype=torch.int32, device=dev)
         i = torch.tensor([r.item for r in chunk], dtype=torch.int32, device=dev)
         rt = torch.tensor([r.rating for r in chunk], dtype=torch.float32, device=dev)
-        q = model.users[u.long()].contiguous()                       # world == 1: slot == user id
-        sc, ids = DeviceTopK(model.items.local[:numItems]).topk(want, q_local=q)
-        sc, ids = sc.cpu().tolist(), ids.cpu().tolist()
-        for j, r in enumerate(chunk):
-            rows.append((r.user, r.item, r.getEventTime(), list(zip(sc[j], ids[j]))))
-        model.step(u, i, rt)
-    model.check_finite()
-    out = _ListWithModel(_seen_filter(rows, K, userMemory))
-    out.model = model
+        # 1 + 2: local top-workerK of every query on this rank's items, gathered + merged on rank 0
+        sc, ids = serving.topk(u.long(), want, workerK=wk, dst=0)
+        if sc is not None:
+            sc, ids = sc.cpu().tolist(), ids.cpu().tolist()
+            for j, r in enumerate(chunk):
+                rows.append((r.user, r.item, r.getEventTime(),
+                             [(s_, i_) for s_, i_ in zip(sc[j], ids[j]) if i_ >= 0 and s_ > -1.0e38]))
+        users.barrier()                      # every rank has read the pre-update user vectors
+        # 3: owner-only item update + pushed user delta (fused kernel, roles swapped)
+        mine = (i % world) == rank
+        ti = torch.where(mine, i, torch.full_like(i, -1))
+        tu, tr = u, rt
+        if negativeSampleRate > 0 and n_valid > 0:
+            # negatives for the owned positives, drawn from the owner's items (reference: <= 32 retries to
+            # avoid the positive; here a colliding draw is shifted to the next local item)
+            neg_slot = torch.randint(0, n_valid, (len(chunk), negativeSampleRate), generator=gen, device=dev)
+            neg_item = (neg_slot * world + rank).to(torch.int32)
+            clash = neg_item == i[:, None]
+            neg_item = torch.where(clash, ((neg_slot + 1) % n_valid * world + rank).to(torch.int32), neg_item)
+            neg_item = torch.where(mine[:, None], neg_item, torch.full_like(neg_item, -1))
+            ti = torch.cat([ti, neg_item.reshape(-1)])
+            tu = torch.cat([u, u[:, None].expand(-1, negativeSampleRate).reshape(-1)])
+            tr = torch.cat([rt, torch.zeros(neg_item.numel(), device=dev)])
+        native.mf_sgd_fused(ti.contiguous(), tu.contiguous(), tr.contiguous(), items, world, users.table_c,
+                            learningRate, err_mode=err_mode, stats=stats, nan_flag=nan_flag,
+                            max_inflight_rows=int(pullLimit or 0), kernel="reg")
+        users.barrier()                      # pushes of this micro-batch are in the PS before the next pulls
+    if int(nan_flag.item()) != 0:
+        from ...errors import FactorIsNotANumberException
+
+        raise FactorIsNotANumberException("non-finite SGD update")
+    out = _ListWithModel(_seen_filter(rows, K, userMemory) if rank == 0 else [])
+    out.users, out.items, out.item_ids, out.n_items = users, items, local_ids, n_valid
+    out.model = _LearnerModel(users, items, world, rank, numFactors)
+    if getattr(serving, "_p2p_gather", None) is not None:
+        serving._p2p_gather.close()
     return out

@@ -239,9 +239,16 @@ class DistributedTopK:
         self.item_ids = local_item_ids.to(torch.int64)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def topk(self, query_user_ids: torch.Tensor, K: int, workerK: Optional[int] = None):
-        import torch.distributed as dist
+    def _gather_lists(self, sc: torch.Tensor, gids: torch.Tensor, dst):
+        """Partial lists -> the merging rank(s) by one-sided stores into their receive slots
+        (:class:`~fps_b200.parallel.fabric.P2PGather`): no NCCL collective on this path."""
+        from ..._p2p import gather_pair
 
+        return gather_pair(self, sc, gids, dst, self.group, self.users.device)
+
+    def topk(self, query_user_ids: torch.Tensor, K: int, workerK: Optional[int] = None, dst=None):
+        """``dst=None``: every rank gets the merged lists; ``dst=r``: only rank ``r`` merges (the
+        parallelism-1 sink of CollectTopKFromEachWorker.scala:41-56), the others return ``(None, None)``."""
         wk = min(workerK or K, self.local.n_items)
         sc, rows = self.local.topk(wk, q_ids=query_user_ids, q_table=self.users)
         gids = self.item_ids[rows]
@@ -251,8 +258,8 @@ class DistributedTopK:
             pad = (workerK or K) - wk
             sc = torch.nn.functional.pad(sc, (0, pad), value=-3.0e38)
             gids = torch.nn.functional.pad(gids, (0, pad), value=-1)
-        all_sc = [torch.empty_like(sc) for _ in range(self.world)]
-        all_id = [torch.empty_like(gids) for _ in range(self.world)]
-        dist.all_gather(all_sc, sc.contiguous(), group=self.group)
-        dist.all_gather(all_id, gids.contiguous(), group=self.group)
+        got = self._gather_lists(sc.contiguous(), gids.contiguous(), dst)
+        if got is None:
+            return None, None
+        all_sc, all_id = got
         return merge_partial_topk(torch.cat(all_sc, 1), torch.cat(all_id, 1), K)

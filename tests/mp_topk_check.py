@@ -40,6 +40,41 @@ def main():
     assert torch.equal(ids[:, 0], ref_ids[:, 0]) or (sc[:, 0] - ref.values[:, 0]).abs().max() < 2e-2
     users.barrier()
     users.close()
+    # ---- one-sided gather of partial lists (E9) and a 2-shard sketch query over it -----------------------
+    from fps_b200.parallel.fabric import P2PGather
+    pg = P2PGather(1024)
+    for it in range(5):                      # slot reuse + acknowledgements
+        parts = pg.gather(torch.full((7,), float(rank * 10 + it), device=dev), dst=None)
+        assert [int(p[0]) for p in parts] == [r * 10 + it for r in range(world)]
+        only0 = pg.gather(torch.arange(4, device=dev) + rank, dst=0)
+        assert (only0 is None) == (rank != 0)
+        if rank == 0:
+            assert [int(p[0]) for p in only0] == list(range(world))
+    pg.close()
+    from fps_b200.models.sketch.device import DeviceSketch
+    from fps_b200.models.sketch.hashing import java_string_hash
+    from fps_b200.models.sketch.jobs import median_of_means
+    words = [["cat", "dog"], ["cat", "dog", "fish"], ["bird"], ["bird", "fish"], ["cat", "dog"], ["fish"]] * 8
+    tweets = [(2000 + i, ws) for i, ws in enumerate(words)]
+    sk = DeviceSketch("tow", 64, 96)
+    for w in ["cat", "dog", "fish", "bird"]:
+        sk._key(w)                           # same dictionary on every rank
+    sk.update(tweets[rank::world])           # every rank feeds its partition of the stream
+    sk.table.barrier()
+    got = sk.query("cat", 3, num_means=6)
+    full = {}
+    for part in [None] * 1:
+        pass
+    parts = [None] * world
+    dist.all_gather_object(parts, sk.model())
+    for p in parts:
+        full.update(dict(p))
+    target = full[java_string_hash("cat")]
+    host = sorted(((median_of_means(v, target, 96, 6), k) for k, v in full.items()), reverse=True)[:3]
+    assert [k for _, k in got][:2] == [k for _, k in host][:2], (got, host)
+    for (a, _), (b, _) in zip(got, host):
+        assert abs(a - b) < 1e-3 * max(1.0, abs(b))
+    sk.close()
     if rank == 0:
         print("MP_TOPK_CHECK_OK", round(overlap, 4))
     dist.destroy_process_group()

@@ -45,3 +45,7 @@ def test_multi_rank_distributed_topk():
 
 def test_multi_rank_replica_exchange_conservation_and_convergence():
     _run("mp_replica_check.py", _world(), 29619, "MP_REPLICA_CHECK_OK")
+
+
+def test_multi_rank_online_learner_and_topk_generator():
+    _run("mp_learner_check.py", _world(), 29620, "MP_LEARNER_CHECK_OK")
