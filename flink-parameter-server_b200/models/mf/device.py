@@ -45,7 +45,8 @@ class DeviceOnlineMF:
                  sync_every: int = 4, user_memory: int = 0,
                  sync_interval_ms: Optional[float] = None, item_blocking: Optional[bool] = None,
                  block_bytes: int = 16 << 20, flush_count: Optional[int] = None,
-                 flush_require: str = "any", replica_own_inplace: Optional[bool] = None):
+                 flush_require: str = "any", replica_own_inplace: Optional[bool] = None,
+                 output_ring=None):
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cuda_device = torch.device("cuda", self.device)
         self.group = group
@@ -60,6 +61,7 @@ class DeviceOnlineMF:
         self.seed = int(seed)
         self.step_no = 0
         self.kernel = kernel
+        self.output_ring = output_ring     # E5: per-update (user, vector) output stream (runtime/output_ring.py)
         with torch.cuda.device(self.device):
             # parameter server: item vectors, sharded item % psParallelism
             self.items = ShardedTable(num_items, num_factors, partition="hash", group=group,
@@ -144,6 +146,8 @@ class DeviceOnlineMF:
             neg = 0
         n_records = users.numel()
         fed = False
+        ring = self.output_ring
+        out_args = ring.kernel_args() if ring is not None else None
         if self.item_blocking and self.block_buckets > 1:
             hashed = self.item_cache and self.items.mode == native.PART_HASH
             fed = hashed
@@ -160,14 +164,16 @@ class DeviceOnlineMF:
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints,
-                                reserve_total=self.replica.reserve_total())
+                                reserve_total=self.replica.reserve_total(), output=out_args)
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel=self.kernel,
-                                l2_hints=self.l2_hints)
+                                l2_hints=self.l2_hints, output=out_args)
+        if ring is not None:               # device-side count / timer policy + flush to the pinned host ring
+            ring.after_kernel(users.numel() * (1 + neg))
         self.step_no += 1
         METRICS.inc("mf_ratings", users.numel())
 

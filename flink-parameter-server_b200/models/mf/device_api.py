@@ -71,7 +71,11 @@ def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learn
                         negativeSampleRate=0, pullLimit=0, seed=0, plain_residual=False,
                         numUsers: Optional[int] = None, numItems: Optional[int] = None,
                         batch_size: int = 1 << 16, group=None, epochs: int = 1,
-                        userMemory: int = 128) -> ResultStream:
+                        userMemory: int = 128, updateOutput: Optional[int] = None,
+                        outputFlushCount: int = 1, outputFlushMs: Optional[float] = None) -> ResultStream:
+    """``updateOutput=n``: also emit ``Left((userId, userVector))`` for one update in ``n`` (``1`` = every
+    update, the reference's worker output PSOnlineMatrixFactorizationWorker.scala:52) through the device
+    output ring (count / timer flushed on the device); the final dump then holds only the item shard."""
     recs = None
     if numUsers is None or numItems is None:
         recs = list(src.collect() if hasattr(src, "collect") else src)
@@ -87,6 +91,14 @@ def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learn
                            group=group, seed=seed, err_mode=ERR_PLAIN if plain_residual else ERR_SIGMOID,
                            track_touched=True,
                            user_memory=min(int(userMemory), 256) if negativeSampleRate > 0 else 0)
+    ring, updates = None, []
+    if updateOutput:
+        from ...runtime.output_ring import OutputRing
+
+        cap = max(1 << 16, 2 * batch_size * (1 + negativeSampleRate))
+        ring = OutputRing(numFactors, model.cuda_device, ring_capacity=4 * cap, staging_capacity=cap,
+                          every=int(updateOutput), flush_count=outputFlushCount, flush_interval_ms=outputFlushMs)
+        model.output_ring = ring
     seen = set()
     data = list(_batches(src, batch_size))
     for b in data:
@@ -94,9 +106,18 @@ def ps_online_mf_device(src, numFactors=10, rangeMin=-0.01, rangeMax=0.01, learn
             seen.update(b[0].tolist())
     for _ in range(max(1, epochs)):
         for _loss in model.fit_stream(iter(data)):
-            pass
+            if ring is not None:
+                updates.extend(ring.records())
     model.check_finite()
     model.barrier()
+    if ring is not None:
+        ring.flush()
+        torch.cuda.synchronize(model.cuda_device)
+        updates.extend(ring.records())
+        res = _result(model, set())               # item shard dump only; user vectors came as the update stream
+        rs = ResultStream(updates + [r for r in res.collect() if r.is_right])
+        rs.model, rs.output_ring = model, ring
+        return rs
     return _result(model, seen if seen else None)
 
 

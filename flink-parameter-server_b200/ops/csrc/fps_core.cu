@@ -69,7 +69,7 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
 // chosen by the host from pullLimit (credits pre-distributed to resident lane-groups).
 // ----------------------------------------------------------------------------------------
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0>
 __global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
   unsigned long long pol_user = 0, pol_item = 0;
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256, MINB)
     float* pp[R];
     float rt[R];
     bool ok[R];
+    long long uid[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const long long idx = base + (long long)r * n_groups + group;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256, MINB)
           item = (IdT)neg;
         }
       }
+      uid[r] = (long long)user;
       up[r] = a.user_sharded ? fps_row_t<IdT>(a.user_tab, user)
                              : a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
       vp[r] = fps_row_t<IdT>(a.item_tab, item);
@@ -176,12 +178,24 @@ __global__ void __launch_bounds__(256, MINB)
           sq_acc += resid * resid;
           cnt_acc += 1.f;
         }
+        long long out_slot = -1;
+        if (EMIT) {   // E5: this update's view of the new user vector goes to the output staging area
+          const long long idx = base + (long long)r * n_groups + group;
+          if (idx % a.out_every == 0) {
+            out_slot = (long long)*a.out_staged + idx / a.out_every;
+            if (out_slot >= a.out_cap) out_slot = -1;
+            else if (lane == 0) a.out_ids[out_slot] = uid[r];
+          }
+        }
 #pragma unroll
         for (int c = 0; c < VPL; ++c) {
           const int q = lane + c * LPR;
           if (q < nvec) {
             float4 du = make_float4(g * v[r][c].x, g * v[r][c].y, g * v[r][c].z, g * v[r][c].w);
             float4 dv = make_float4(g * u[r][c].x, g * u[r][c].y, g * u[r][c].z, g * u[r][c].w);
+            if (EMIT && out_slot >= 0)
+              *reinterpret_cast<float4*>(a.out_vecs + out_slot * (long long)stride + 4 * q) =
+                  make_float4(u[r][c].x + du.x, u[r][c].y + du.y, u[r][c].z + du.z, u[r][c].w + du.w);
             if (HINT) {
               fps_red_add4_hint(up[r] + 4 * q, du, pol_user);
               fps_red_add4_hint(pp[r] + 4 * q, dv, pol_item);
@@ -212,13 +226,13 @@ static int g_mf_reserve_total = 0;  // CTA slots left free on the whole GPU (the
 extern "C" void fps_set_mf_reserve(int v) { g_mf_reserve = v < 0 ? 0 : v; }
 extern "C" void fps_set_mf_reserve_total(int v) { g_mf_reserve_total = v < 0 ? 0 : v; }
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
   const int groups_per_block = threads / LPR;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT>, threads, 0);
+      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT>, threads, 0);
   occ -= g_mf_reserve;  // leave slots for the background replica exchange (see fps_cache_sync)
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ - g_mf_reserve_total;
@@ -233,7 +247,7 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
   if (need < 1) need = 1;
   if (blocks > need) blocks = need;
-  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT><<<(int)blocks, threads, 0, stream>>>(a);
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT><<<(int)blocks, threads, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -246,6 +260,15 @@ template <typename IdT, int FMT>
 static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
   const int nvec = a.item_tab.stride >> 2;
   const int v = g_mf_reg_variant;
+  if (a.out_every > 0) {   // with the E5 output stream (one row in flight per lane-group, 4 CTAs/SM)
+    if (a.out_ids == nullptr || a.out_vecs == nullptr || a.out_staged == nullptr) return -1002;
+    if (nvec <= 4) return launch_mf<IdT, 4, 1, 1, 4, FMT, 0, 1>(a, max_inflight, num_sms, s);
+    if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 4, FMT, 0, 1>(a, max_inflight, num_sms, s);
+    if (nvec <= 16) return launch_mf<IdT, 16, 1, 1, 4, FMT, 0, 1>(a, max_inflight, num_sms, s);
+    if (nvec <= 32) return launch_mf<IdT, 32, 1, 1, 4, FMT, 0, 1>(a, max_inflight, num_sms, s);
+    if (nvec <= 128) return launch_mf<IdT, 32, 4, 1, 2, FMT, 0, 1>(a, max_inflight, num_sms, s);
+    return -1000;
+  }
   if (nvec <= 1) return launch_mf<IdT, 1, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
   if (nvec <= 2) return launch_mf<IdT, 2, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);
   if (nvec <= 4) return launch_mf<IdT, 4, 1, 2, 4, FMT>(a, max_inflight, num_sms, s);

@@ -31,4 +31,13 @@ struct MfArgs {
   int pad2_;
   unsigned int* progress;    // optional: CTA 0 publishes the record index it has reached (replica
                              //   exchange kernels follow the sweep over the L2-blocked batch)
+  // E5 worker output stream (ps.output((user, userVector)) after every update,
+  // PSOnlineMatrixFactorizationWorker.scala:52): record idx is emitted iff idx % out_every == 0, into the
+  // device staging area of an OutputRing at slot *out_staged + idx / out_every (dropped beyond out_cap)
+  long long* out_ids;
+  float* out_vecs;
+  const unsigned long long* out_staged;
+  long long out_cap;
+  int out_every;             // 0 = no output stream
+  int pad3_;
 };

@@ -72,6 +72,12 @@ class MfArgsC(C.Structure):
         ("l2_hints", C.c_int),
         ("pad2_", C.c_int),
         ("progress", C.c_void_p),
+        ("out_ids", C.c_void_p),
+        ("out_vecs", C.c_void_p),
+        ("out_staged", C.c_void_p),
+        ("out_cap", C.c_longlong),
+        ("out_every", C.c_int),
+        ("pad3_", C.c_int),
     ]
 
 
@@ -235,7 +241,7 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
                  kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None,
                  l2_hints: bool = False, reserve_ctas: int = 0, reserve_total: int = 0,
-                 progress: Optional[torch.Tensor] = None) -> None:
+                 progress: Optional[torch.Tensor] = None, output=None) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -277,9 +283,13 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
         a.push_tab = push_tab; a.use_push_tab = 1
     a.l2_hints = 1 if l2_hints else 0
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
-    if packed or push_tab is not None or l2_hints:
+    if packed or push_tab is not None or l2_hints or output is not None:
         variant = "reg"
     a.progress = progress.data_ptr() if progress is not None else None
+    if output is not None:     # E5 worker output stream: (out_ids, out_vecs, staged counter, capacity, every)
+        o_ids, o_vecs, o_staged, o_cap, o_every = output
+        a.out_ids = o_ids.data_ptr(); a.out_vecs = o_vecs.data_ptr(); a.out_staged = o_staged.data_ptr()
+        a.out_cap = int(o_cap); a.out_every = int(o_every)
     lib().fps_set_mf_reserve(int(reserve_ctas))
     lib().fps_set_mf_reserve_total(int(reserve_total))
     rv = os.environ.get("FPS_MF_REG_VARIANT")
@@ -473,6 +483,40 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
     tc.rows_per_shard = t.shape[0]; tc.div = t.shape[0]; tc.num_shards = 1
     tc.dim = int(dim); tc.stride = t.shape[1]; tc.mode = PART_HASH; tc.shard_shift = 0
     return tc
+
+
+class OutPolicyC(C.Structure):
+    """Mirror of ``struct OutPolicy`` (csrc/fps_output.cu)."""
+
+    _fields_ = [("count_max", C.c_ulonglong), ("interval_ns", C.c_ulonglong), ("n_new", C.c_ulonglong),
+                ("staging_cap", C.c_ulonglong), ("ring_cap", C.c_ulonglong), ("require_all", C.c_int),
+                ("force", C.c_int)]
+
+
+OUT_STATE_WORDS = 8     # int64 words of ``struct OutState``
+
+
+def output_step(state: torch.Tensor, s_ids: torch.Tensor, s_vecs: torch.Tensor, ring_ids: torch.Tensor,
+                ring_vecs: torch.Tensor, host_tail: torch.Tensor, host_head: torch.Tensor, *, n_new: int,
+                count_max: int = 0, interval_ns: int = 0, require_all: bool = False,
+                force: bool = False) -> None:
+    """Device-side count / timer flush policy of the worker output stream followed by the flush kernel
+    (staging area -> ring in pinned host memory, tail published with ``st.release.sys``).  The ring and
+    the head / tail words are pinned host tensors (mapped); csrc/fps_output.cu."""
+    _req(state, "state", torch.int64); _req(s_ids, "s_ids", torch.int64); _req(s_vecs, "s_vecs", torch.float32)
+    for t, nm in ((ring_ids, "ring_ids"), (ring_vecs, "ring_vecs"), (host_tail, "host_tail"), (host_head, "host_head")):
+        if t.is_cuda or not t.is_pinned():
+            raise ValueError(f"{nm} must be a pinned host tensor")
+    p = OutPolicyC()
+    p.count_max = int(count_max); p.interval_ns = int(interval_ns); p.n_new = int(n_new)
+    p.staging_cap = int(s_ids.numel()); p.ring_cap = int(ring_ids.numel())
+    p.require_all = int(bool(require_all)); p.force = int(bool(force))
+    _check(lib().fps_output_step(C.byref(p), C.c_void_p(state.data_ptr()), C.c_void_p(s_ids.data_ptr()),
+                                 C.c_void_p(s_vecs.data_ptr()), int(s_vecs.shape[1]),
+                                 C.c_void_p(ring_ids.data_ptr()), C.c_void_p(ring_vecs.data_ptr()),
+                                 C.c_void_p(host_tail.data_ptr()), C.c_void_p(host_head.data_ptr()),
+                                 sm_count(state.device.index), _stream()), "output_step")
+    _bump(2)
 
 
 class FlushPolicyC(C.Structure):
