@@ -61,6 +61,9 @@ class DeviceOnlineMF:
         self.seed = int(seed)
         self.step_no = 0
         self.kernel = kernel
+        # pull limiter (WL:196-250) = device credit counter [credits, stalls] consumed inside the fused kernel
+        self.credits = (torch.tensor([self.pull_limit, 0], dtype=torch.int32, device=self.cuda_device)
+                        if self.pull_limit > 0 and os.environ.get("FPS_STATIC_LIMITER", "0") != "1" else None)
         self.output_ring = output_ring     # E5: per-update (user, vector) output stream (runtime/output_ring.py)
         with torch.cuda.device(self.device):
             # parameter server: item vectors, sharded item % psParallelism
@@ -164,14 +167,15 @@ class DeviceOnlineMF:
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel="reg", l2_hints=self.l2_hints,
-                                reserve_total=self.replica.reserve_total(), output=out_args)
+                                reserve_total=self.replica.reserve_total(), output=out_args,
+                                credits=self.credits)
         else:
             native.mf_sgd_fused(users, items, ratings, self.users, self.world, self.items.table_c,
                                 self.lr, err_mode=self.err_mode, neg_rate=neg,
                                 num_items=self.num_items, seed=self.seed, step=self.step_no,
                                 stats=self.stats, nan_flag=self.nan_flag,
                                 max_inflight_rows=self.pull_limit, kernel=self.kernel,
-                                l2_hints=self.l2_hints, output=out_args)
+                                l2_hints=self.l2_hints, output=out_args, credits=self.credits)
         if ring is not None:               # device-side count / timer policy + flush to the pinned host ring
             ring.after_kernel(users.numel() * (1 + neg))
         self.step_no += 1

@@ -54,6 +54,20 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
   return (int)cudaGetLastError();
 }
 
+// Device-side pull limiter (WL:196-250 as a credit counter): `credits[0]` holds the number of pulls that
+// may still be issued; a lane-group takes one credit before it touches the owner's memory and returns
+// it when the answer has been consumed (stored), so at most `pullLimit` row pulls are un-answered at any
+// time whatever the grid size.  `credits[1]` counts the stalls (acquisitions that had to wait).
+__device__ __forceinline__ void fps_credit_acquire(int* credits) {
+  bool stalled = false;
+  while (atomicSub(credits, 1) <= 0) {
+    atomicAdd(credits, 1);
+    stalled = true;
+    __nanosleep(128);
+  }
+  if (stalled) atomicAdd(credits + 1, 1);
+}
+
 // ----------------------------------------------------------------------------------------
 // K1+K3+K2: fused matrix-factorisation step.
 //   for each (user, item, rating):          [+ neg_rate sampled (user, item', 0)]
@@ -69,9 +83,10 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
 // chosen by the host from pullLimit (credits pre-distributed to resident lane-groups).
 // ----------------------------------------------------------------------------------------
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0, int LIMIT = 0>
 __global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) & ~(LPR - 1)));
   unsigned long long pol_user = 0, pol_item = 0;
   if (HINT) {
     pol_user = fps_policy_evict_first();
@@ -138,6 +153,10 @@ __global__ void __launch_bounds__(256, MINB)
         }
       }
       uid[r] = (long long)user;
+      if (LIMIT) {   // take a pull credit before touching the owner; returned once the push is issued
+        if (lane == 0 && ok[r]) fps_credit_acquire(a.credits);
+        __syncwarp(gmask);
+      }
       up[r] = a.user_sharded ? fps_row_t<IdT>(a.user_tab, user)
                              : a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
       vp[r] = fps_row_t<IdT>(a.item_tab, item);
@@ -172,6 +191,10 @@ __global__ void __launch_bounds__(256, MINB)
                       : (a.err_mode == 1) ? resid
                                           : rt[r] - 1.f / (1.f + __expf(-d));
       const float g = a.lr * e;
+      if (LIMIT) {
+        __syncwarp(gmask);                          // every lane holds its part of the answer
+        if (lane == 0 && ok[r]) atomicAdd(a.credits, 1);
+      }
       if (ok[r]) {
         if (!(fabsf(g) <= 3.0e38f)) bad = true;  // NaN/Inf guard (Vector.scala:78-80)
         if (lane == 0) {
@@ -226,13 +249,13 @@ static int g_mf_reserve_total = 0;  // CTA slots left free on the whole GPU (the
 extern "C" void fps_set_mf_reserve(int v) { g_mf_reserve = v < 0 ? 0 : v; }
 extern "C" void fps_set_mf_reserve_total(int v) { g_mf_reserve_total = v < 0 ? 0 : v; }
 
-template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0>
+template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0, int LIMIT = 0>
 static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaStream_t stream) {
   const int threads = 256;
   const int groups_per_block = threads / LPR;
   int occ = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT>, threads, 0);
+      &occ, fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT, LIMIT>, threads, 0);
   occ -= g_mf_reserve;  // leave slots for the background replica exchange (see fps_cache_sync)
   if (occ < 1) occ = 1;
   long long blocks = (long long)num_sms * occ - g_mf_reserve_total;
@@ -247,7 +270,7 @@ static int launch_mf(const MfArgs& a, int max_inflight_rows, int num_sms, cudaSt
   long long need = (n_eff + (long long)groups_per_block * R - 1) / ((long long)groups_per_block * R);
   if (need < 1) need = 1;
   if (blocks > need) blocks = need;
-  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT><<<(int)blocks, threads, 0, stream>>>(a);
+  fps_mf_sgd_fused_kernel<IdT, LPR, VPL, R, MINB, FMT, HINT, EMIT, LIMIT><<<(int)blocks, threads, 0, stream>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -260,6 +283,14 @@ template <typename IdT, int FMT>
 static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
   const int nvec = a.item_tab.stride >> 2;
   const int v = g_mf_reg_variant;
+  if (a.credits != nullptr) {   // device credit-counter pull limiter: full grid, the counter bounds the pulls in flight
+    if (nvec <= 4) return launch_mf<IdT, 4, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
+    if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
+    if (nvec <= 16) return launch_mf<IdT, 16, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
+    if (nvec <= 32) return launch_mf<IdT, 32, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
+    if (nvec <= 128) return launch_mf<IdT, 32, 4, 1, 2, FMT, 0, 0, 1>(a, 0, num_sms, s);
+    return -1000;
+  }
   if (a.out_every > 0) {   // with the E5 output stream (one row in flight per lane-group, 4 CTAs/SM)
     if (a.out_ids == nullptr || a.out_vecs == nullptr || a.out_staged == nullptr) return -1002;
     if (nvec <= 4) return launch_mf<IdT, 4, 1, 1, 4, FMT, 0, 1>(a, max_inflight, num_sms, s);
@@ -306,20 +337,6 @@ extern "C" int fps_mf_sgd_fused(const MfArgs* args, int id_bytes, int max_inflig
 // pull_dot:      score[i] = table[ids[i], :] . local[i, :]   (pull fused with the consumer)
 // One lane-group of LPR lanes per row, VPL chunks per lane, generic in dim via nvec bound.
 // ----------------------------------------------------------------------------------------
-// Device-side pull limiter (WL:196-250 as a credit counter): `credits[0]` holds the number of pulls that
-// may still be issued; a lane-group takes one credit before it touches the owner's memory and returns
-// it when the answer has been consumed (stored), so at most `pullLimit` row pulls are un-answered at any
-// time whatever the grid size.  `credits[1]` counts the stalls (acquisitions that had to wait).
-__device__ __forceinline__ void fps_credit_acquire(int* credits) {
-  bool stalled = false;
-  while (atomicSub(credits, 1) <= 0) {
-    atomicAdd(credits, 1);
-    stalled = true;
-    __nanosleep(128);
-  }
-  if (stalled) atomicAdd(credits + 1, 1);
-}
-
 template <typename IdT, int LPR>
 __global__ void __launch_bounds__(256)
     fps_pull_gather_kernel(const __grid_constant__ ShardTable t, const IdT* __restrict__ ids,

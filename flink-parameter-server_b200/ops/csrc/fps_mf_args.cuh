@@ -40,4 +40,6 @@ struct MfArgs {
   long long out_cap;
   int out_every;             // 0 = no output stream
   int pad3_;
+  int* credits;              // device-side pull limiter (WL:196-250): credits[0] = pulls that may still be
+                             //   issued, credits[1] = stall counter; nullptr = unlimited
 };

@@ -78,6 +78,7 @@ class MfArgsC(C.Structure):
         ("out_cap", C.c_longlong),
         ("out_every", C.c_int),
         ("pad3_", C.c_int),
+        ("credits", C.c_void_p),
     ]
 
 
@@ -241,7 +242,8 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
                  nan_flag: Optional[torch.Tensor] = None, max_inflight_rows: int = 0,
                  kernel: Optional[str] = None, push_tab: Optional[ShardTableC] = None,
                  l2_hints: bool = False, reserve_ctas: int = 0, reserve_total: int = 0,
-                 progress: Optional[torch.Tensor] = None, output=None) -> None:
+                 progress: Optional[torch.Tensor] = None, output=None,
+                 credits: Optional[torch.Tensor] = None) -> None:
     """Fused pull + SGD + push (K1+K3+K2).
 
     ``kernel="reg"`` (default): register-staged loads at full occupancy (csrc/fps_core.cu);
@@ -283,9 +285,12 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
         a.push_tab = push_tab; a.use_push_tab = 1
     a.l2_hints = 1 if l2_hints else 0
     variant = kernel or os.environ.get("FPS_MF_KERNEL", "reg")
-    if packed or push_tab is not None or l2_hints or output is not None:
+    if packed or push_tab is not None or l2_hints or output is not None or credits is not None:
         variant = "reg"
     a.progress = progress.data_ptr() if progress is not None else None
+    if credits is not None:    # device-side credit-counter pull limiter (int32 [credits, stalls])
+        _req(credits, "credits", torch.int32)
+        a.credits = credits.data_ptr()
     if output is not None:     # E5 worker output stream: (out_ids, out_vecs, staged counter, capacity, every)
         o_ids, o_vecs, o_staged, o_cap, o_every = output
         a.out_ids = o_ids.data_ptr(); a.out_vecs = o_vecs.data_ptr(); a.out_staged = o_staged.data_ptr()

@@ -2,8 +2,9 @@
 
 ``NcclOnlineMF`` has the API of :class:`DeviceOnlineMF` but implements one micro-batch as
 
-    bucket item ids by owner -> all_to_all(ids) -> owners gather rows -> all_to_all(values)
-    -> elementwise SGD kernels -> all_to_all(deltas) -> owners index_add_
+    sort item ids by owner into fixed-capacity slots -> all_to_all(ids) -> owners gather rows ->
+    all_to_all(values) -> elementwise SGD kernels -> all_to_all(deltas) -> owners index_add_
+    (equal-split collectives: no size exchange, no host synchronisation inside a step)
 
 i.e. exactly "a path that only calls NCCL for pull/push" with stock PyTorch kernels in between:
 the baseline the fused one-sided kernels are measured against (``bench.py --impl nccl``).  With
@@ -53,6 +54,8 @@ class NcclOnlineMF:
         self.item_shard = _uniform_by_id(item_ids, self.k, seed * 2 + 1, range_min, range_max)
         self.users = _uniform_by_id(user_ids, self.k, seed * 2 + 2, range_min, range_max)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.overflow = torch.zeros((), dtype=torch.bool, device=self.dev)
+        self._n_cap = 0
         self.launches = 0
 
     # -- collectives ------------------------------------------------------------------------
@@ -64,45 +67,93 @@ class NcclOnlineMF:
                                input_split_sizes=list(send_counts), group=self.group)
         return out
 
-    def step(self, users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor) -> None:
+    def _slots(self, n: int) -> int:
+        """Fixed per-destination capacity of the exchange buffers: mean + 6 sigma of a uniform split, so the
+        collectives need no size exchange (no host synchronisation per step); overflow is flagged."""
         W = self.world
+        if W == 1:
+            return n
+        if n > self._n_cap:       # first step (or a larger batch): agree on the capacity once, collectively
+            t = torch.tensor([n], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._n_cap = int(t.item())
+        mean = self._n_cap / W
+        return int(mean + 6.0 * (mean * (1.0 - 1.0 / W)) ** 0.5 + 16)
+
+    def step(self, users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor) -> None:
+        """One micro-batch with collectives + stock kernels and NO host synchronisation:
+        owner-sort -> fixed-capacity send slots -> all_to_all(ids) -> gather -> all_to_all(rows)
+        -> elementwise SGD -> index_add (users) -> all_to_all(deltas) -> index_add (item shard)."""
+        W, k = self.world, self.k
+        n = items.numel()
+        C = self._slots(n)
         items64 = items.to(torch.int64)
         owner = items64 % W
         order = torch.argsort(owner, stable=True)
-        send_ids = items64[order]
-        send_counts = torch.bincount(owner, minlength=W)
-        if W > 1:
-            recv_counts = torch.empty_like(send_counts)
-            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-            sc, rc = send_counts.tolist(), recv_counts.tolist()
-        else:
-            sc = rc = send_counts.tolist()
+        so = owner[order]
+        counts = torch.bincount(owner, minlength=W)
+        start = torch.cumsum(counts, 0) - counts
+        pos = torch.arange(n, device=self.dev) - start[so]                 # rank inside the owner group
+        self.overflow |= (counts.max() > C)
+        keep = pos < C
+        slot = (so * C + pos)[keep]
+        src = order[keep]
+        send_ids = torch.full((W * C,), -1, dtype=torch.int64, device=self.dev)
+        send_ids[slot] = items64[src]
         # PULL: request ids -> owners gather -> answers
-        req = self._a2a(send_ids, sc, rc)
-        rows = self.item_shard[req // W]
-        v_sorted = self._a2a(rows, rc, sc)
-        # worker compute (separate elementwise kernels)
-        uslot = users.to(torch.int64)[order] // W
+        req = self._a2a_eq(send_ids)
+        valid_req = req >= 0
+        rows = self.item_shard[torch.where(valid_req, req // W, torch.zeros_like(req))]
+        v = self._a2a_eq(rows)                                            # [W*C, k] answers, slot order
+        # worker compute (separate elementwise kernels) on the padded slots
+        uslot = torch.zeros(W * C, dtype=torch.int64, device=self.dev)
+        uslot[slot] = users.to(torch.int64)[src] // W
+        r = torch.zeros(W * C, dtype=torch.float32, device=self.dev)
+        r[slot] = ratings[src]
+        live = send_ids >= 0
         u = self.users[uslot]
-        r = ratings[order]
-        resid = r - (u * v_sorted).sum(1)
+        resid = r - (u * v).sum(1)
         e = torch.sigmoid(resid) if self.err_mode == ERR_SIGMOID else resid
-        g = (self.lr * e)[:, None]
-        self.users.index_add_(0, uslot, g * v_sorted)
+        g = torch.where(live, self.lr * e, torch.zeros_like(e))[:, None]
+        self.users.index_add_(0, uslot, g * v)
         dv = g * u
         # PUSH: deltas -> owners -> paramUpdate
-        dv_recv = self._a2a(dv, sc, rc)
-        self.item_shard.index_add_(0, req // W, dv_recv)
-        self.stats[0] += (resid * resid).sum()
-        self.stats[1] += float(resid.numel())
+        dv_recv = self._a2a_eq(dv)
+        self.item_shard.index_add_(0, torch.where(valid_req, req // W, torch.zeros_like(req)),
+                                   torch.where(valid_req[:, None], dv_recv, torch.zeros_like(dv_recv)))
+        live_f = live.float()
+        self.stats[0] += (resid * resid * live_f).sum()
+        self.stats[1] += live_f.sum()
+
+    def _a2a_eq(self, send: torch.Tensor) -> torch.Tensor:
+        """all_to_all with equal splits (no size exchange)."""
+        if self.world == 1:
+            return send
+        out = torch.empty_like(send)
+        dist.all_to_all_single(out, send, group=self.group)
+        return out
 
     def fit_stream(self, host_batches: Iterable[Sequence[torch.Tensor]]):
+        """Every batch copied from (pinned) host memory, the step's loss read back one step late."""
+        pending = []
         for (u, i, r) in host_batches:
             self.stats.zero_()
             self.step(u.to(self.dev, non_blocking=True), i.to(self.dev, non_blocking=True),
                       r.to(self.dev, non_blocking=True))
-            s = self.stats.cpu()
-            yield float(s[0]), float(s[1])
+            if self.dev.type == "cuda":
+                h = torch.empty(2, dtype=torch.float32).pin_memory()
+                h.copy_(self.stats, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record()
+                pending.append((h, ev))
+                if len(pending) > 2:
+                    h0, e0 = pending.pop(0); e0.synchronize()
+                    yield float(h0[0]), float(h0[1])
+            else:
+                s = self.stats.clone()
+                yield float(s[0]), float(s[1])
+        for h0, e0 in pending:
+            e0.synchronize()
+            yield float(h0[0]), float(h0[1])
 
     def predict(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
         W = self.world
@@ -124,6 +175,8 @@ class NcclOnlineMF:
         return out
 
     def check_finite(self) -> None:
+        if bool(self.overflow):
+            raise RuntimeError("NCCL baseline: an exchange slot overflowed (raise the slot capacity)")
         if not torch.isfinite(self.item_shard).all():
             raise FloatingPointError("non-finite item factors")
 

@@ -263,3 +263,26 @@ def test_device_credit_counter_pull_limiter():
     c = t._credits(64, dev)
     assert int(c[0]) == 64 and int(c[1]) > 0                  # every credit returned; the limiter did stall
     t.close()
+
+
+@gpu
+def test_fused_mf_kernel_consumes_the_device_credit_counter():
+    """pullLimit inside the fused pull+SGD+push kernel is a device credit counter (WL:196-250), not launch
+    geometry: same result as the unlimited kernel on a conflict-free batch, every credit returned."""
+    from fps_b200.models.mf.device import DeviceOnlineMF
+
+    dev = torch.device("cuda", 0)
+    nu, ni, k, b = 6000, 5000, 64, 3000
+    free = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5)
+    lim = DeviceOnlineMF(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=0.05, seed=5, pull_limit=64)
+    g = torch.Generator().manual_seed(1)
+    users = torch.randperm(nu, generator=g)[:b].int().to(dev)
+    items = torch.randperm(ni, generator=g)[:b].int().to(dev)
+    ratings = torch.rand(b, generator=g).to(dev)
+    free.step(users, items, ratings); lim.step(users, items, ratings)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(lim.users, free.users, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(lim.items.local, free.items.local, rtol=1e-6, atol=1e-7)
+    assert lim.credits.tolist()[0] == 64 and lim.credits.tolist()[1] > 0
+    assert lim.stats[1].item() == b
+    free.close(); lim.close()
