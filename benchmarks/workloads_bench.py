@@ -64,6 +64,8 @@ def main():
     y = (torch.rand(a.ctr_batch, generator=g) < 0.3).float().to(dev)
     ms = timed(lambda: ctr.step(ids, y), a.steps)
     res["ctr"] = {"slots": a.slots, "fields": 26, "emb_dim": 8, "pull_limit": 64, "batch": a.ctr_batch,
+                  "limiter": "device credit counter inside the gather kernel", "credit_stalls": ctr.credit_stalls(),
+                  "tower": "fused hand-written kernel (fps_ctr.cu), loss kept on the device",
                   "n_gpus": world, "ms_per_step": ms, "examples_per_s": a.ctr_batch * world / ms * 1e3}
     ctr.close()
     if rank == 0:

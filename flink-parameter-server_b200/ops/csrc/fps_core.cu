@@ -60,10 +60,17 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
 // time whatever the grid size.  `credits[1]` counts the stalls (acquisitions that had to wait).
 __device__ __forceinline__ void fps_credit_acquire(int* credits) {
   bool stalled = false;
-  while (atomicSub(credits, 1) <= 0) {
-    atomicAdd(credits, 1);
+  unsigned ns = 256;
+  while (true) {
+    // look before taking: waiters poll with a plain load and back off exponentially, so the counter's
+    // atomic unit stays available for the releases that make progress possible
+    if (*reinterpret_cast<volatile int*>(credits) > 0) {
+      if (atomicSub(credits, 1) > 0) break;
+      atomicAdd(credits, 1);
+    }
     stalled = true;
-    __nanosleep(128);
+    __nanosleep(ns);
+    if (ns < 8192) ns <<= 1;
   }
   if (stalled) atomicAdd(credits + 1, 1);
 }

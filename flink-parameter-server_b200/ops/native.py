@@ -490,6 +490,47 @@ def local_table(t: torch.Tensor, dim: int) -> ShardTableC:
     return tc
 
 
+class CtrArgsC(C.Structure):
+    """Mirror of ``struct CtrArgs`` (csrc/fps_ctr.cu)."""
+
+    _fields_ = [("rows", C.c_void_p), ("labels", C.c_void_p), ("batch", C.c_longlong), ("fields", C.c_int),
+                ("emb", C.c_int), ("stride", C.c_int), ("W1", C.c_void_p), ("W1T", C.c_void_p),
+                ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("gW1", C.c_void_p),
+                ("gb1", C.c_void_p), ("gw2", C.c_void_p), ("gb2", C.c_void_p), ("d_rows", C.c_void_p),
+                ("loss", C.c_void_p), ("prob", C.c_void_p), ("lr", C.c_float), ("train", C.c_int)]
+
+
+CTR_HIDDEN = 256
+
+
+def ctr_step(rows: torch.Tensor, labels: torch.Tensor, fields: int, emb: int, weights: dict, grads: dict,
+             d_rows: Optional[torch.Tensor], loss: torch.Tensor, lr: float, train: bool = True,
+             prob: Optional[torch.Tensor] = None) -> None:
+    """Fused wide-&-deep tower: forward, BCE, backward, dense SGD (mean gradient) and the row gradients
+    (``-lr * dLoss/drow``, ready to push) in one kernel + a small apply kernel.  ``weights``: W1 [IN, 256],
+    W1T [256, IN], b1 [256], w2 [256], b2 [1]; ``grads``: same shapes minus W1T.  csrc/fps_ctr.cu."""
+    _req(rows, "rows", torch.float32); _req(labels, "labels", torch.float32); _req(loss, "loss", torch.float32)
+    a = CtrArgsC()
+    a.rows = rows.data_ptr(); a.labels = labels.data_ptr(); a.batch = labels.numel()
+    a.fields, a.emb, a.stride = int(fields), int(emb), int(rows.shape[1])
+    assert rows.shape[0] == labels.numel() * fields
+    for k in ("W1", "W1T", "b1", "w2", "b2"):
+        _req(weights[k], k, torch.float32)
+        setattr(a, k, weights[k].data_ptr())
+    if train:
+        _req(d_rows, "d_rows", torch.float32)
+        a.gW1, a.gb1, a.gw2, a.gb2 = (grads[k].data_ptr() for k in ("W1", "b1", "w2", "b2"))
+        a.d_rows = d_rows.data_ptr()
+    a.loss = loss.data_ptr()
+    a.prob = prob.data_ptr() if prob is not None else None
+    a.lr = float(lr); a.train = int(bool(train))
+    _check(lib().fps_ctr_step(C.byref(a), C.c_void_p(weights["W1"].data_ptr()),
+                              C.c_void_p(weights["W1T"].data_ptr()), C.c_void_p(weights["b1"].data_ptr()),
+                              C.c_void_p(weights["w2"].data_ptr()), C.c_void_p(weights["b2"].data_ptr()),
+                              sm_count(rows.device.index), _stream()), "ctr_step")
+    _bump(2 if train else 1)
+
+
 class OutPolicyC(C.Structure):
     """Mirror of ``struct OutPolicy`` (csrc/fps_output.cu)."""
 
