@@ -125,15 +125,16 @@ class ClockSampler:
                 "samples": len(inside), "window": window, "reasons": reasons}
 
 
-def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN, sync_list=None):
+def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN, sync_list=None, checkpoints=None):
     """Same synthetic low-rank rating stream, same update budget, plain-residual SGD: N workers in
-    replica mode, N workers in direct one-sided mode, and ONE worker alone; held-out RMSE of each."""
+    replica mode, N workers in direct one-sided mode, and ONE worker alone; held-out RMSE of each
+    (``checkpoints``: budgets, in updates per user, at which the RMSE is evaluated)."""
     import torch
     import torch.distributed as dist
     from fps_b200.utils.synthetic import lowrank_ratings
 
-    budget = a.quality_updates_per_user * a.users
-    steps = max(8, int(budget / (a.batch * world)))
+    cps = sorted(checkpoints or [a.quality_updates_per_user])
+    steps_at = [max(8, int(c * a.users / (a.batch * world))) for c in cps]
     init = a.quality_init
 
     def batch_of(rid, step):
@@ -158,44 +159,56 @@ def quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN, syn
                 dist.all_reduce(t)
         return float((t[0] / t[1]).sqrt())
 
+    def curve(model, w, r, batches_of_step):
+        out, done = [], 0
+        for n in steps_at:
+            for s in range(done, n):
+                for b in batches_of_step(s):
+                    model.step(*b)
+            done = n
+            model.refresh()
+            model.check_finite()
+            out.append(rmse(model, w, r))
+        return out
+
     kw = dict(learning_rate=a.quality_lr, range_min=-init, range_max=init, seed=4321, err_mode=ERR_PLAIN)
     out = {"update_rule": "plain residual e = r - u.v", "lr": a.quality_lr, "init": init,
-           "data": "rank-8 synthetic ratings (utils/synthetic.py), std 0.5", "steps_per_worker": steps,
-           "updates": steps * a.batch * world, "rmse_untrained": float(hr.std())}
+           "data": "rank-8 synthetic ratings (utils/synthetic.py), std 0.5", "updates_per_user": cps,
+           "steps_per_worker": steps_at, "updates": [n * a.batch * world for n in steps_at],
+           "rmse_untrained": float(hr.std())}
+    curves = {}
     if world > 1:
-        runs = [("direct", False, a.sync_every), ("replica", True, a.sync_every)]
+        runs = [("direct", False, a.sync_every)] if not getattr(a, "skip_direct_quality", False) else []
+        runs += [("replica", True, a.sync_every)]
         runs += [(f"replica_sync{se}", True, se) for se in (sync_list or []) if se != a.sync_every]
         for mode, cache, se in runs:
             m = DeviceOnlineMF(a.users, a.items, a.factors, item_cache=cache, sync_every=se, **kw)
-            for s in range(steps):
-                m.step(*batch_of(rank, s))
-            m.refresh()
-            m.check_finite()
-            out["rmse_" + mode] = rmse(m, world, rank)
+            curves[mode] = curve(m, world, rank, lambda s: [batch_of(rank, s)])
             m.barrier(); m.close(); del m
         groups = [dist.new_group([r]) for r in range(world)]
         solo = DeviceOnlineMF(a.users, a.items, a.factors, group=groups[rank], **kw) if rank == 0 else None
     else:
         solo = DeviceOnlineMF(a.users, a.items, a.factors, **kw)
-    ref = torch.zeros(1, dtype=torch.float64, device="cpu" if shared_gpu else dev)
+    ref = torch.zeros(len(cps), dtype=torch.float64, device="cpu" if shared_gpu else dev)
     if rank == 0:
-        for s in range(steps):
-            for rid in range(world):
-                solo.step(*batch_of(rid, s))
-        solo.check_finite()
-        ref[0] = rmse(solo, 1, 0)
+        c = curve(solo, 1, 0, lambda s: [batch_of(rid, s) for rid in range(world)])
+        ref[:] = torch.tensor(c, dtype=torch.float64)
         solo.close()
     if world > 1:
         dist.all_reduce(ref)
-    out["rmse_single_worker"] = float(ref[0])
+    curves["single_worker"] = [float(x) for x in ref]
+    single = curves["single_worker"]
+    for k, v in curves.items():
+        out["rmse_" + k] = v if len(cps) > 1 else v[0]
     if world > 1:
-        for k in [k for k in out if k.startswith("rmse_replica_sync")]:
-            out[k.replace("rmse_", "") + "_vs_single"] = out[k] / out["rmse_single_worker"]
         out["sync_every"] = a.sync_every
-        out["replica_vs_single"] = out["rmse_replica"] / out["rmse_single_worker"]
-        out["direct_vs_single"] = out["rmse_direct"] / out["rmse_single_worker"]
-        out["within_2pct"] = bool(abs(out["replica_vs_single"] - 1) <= 0.02 and
-                                  abs(out["rmse_replica"] / out["rmse_direct"] - 1) <= 0.02)
+        for k, v in curves.items():
+            if k != "single_worker":
+                ratio = [x / y for x, y in zip(v, single)]
+                out[k + "_vs_single"] = ratio if len(cps) > 1 else ratio[0]
+        r_last = curves["replica"][-1] / single[-1]
+        d_last = (curves["direct"][-1] / single[-1]) if "direct" in curves else None
+        out["within_2pct"] = bool(abs(r_last - 1) <= 0.02 and (d_last is None or abs(d_last - 1) <= 0.02))
     return out
 
 

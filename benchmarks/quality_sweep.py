@@ -24,12 +24,16 @@ def main():
     sync = [1, 2, 4, 8]
     if "--sync" in argv:
         i = argv.index("--sync"); sync = [int(x) for x in argv[i + 1].split(",")]; del argv[i:i + 2]
-    upu = 400.0
-    if "--updates-per-user" in argv:
-        i = argv.index("--updates-per-user"); upu = float(argv[i + 1]); del argv[i:i + 2]
+    upu = [400.0]
+    if "--updates-per-user" in argv:       # comma list = checkpoints of one run per mode
+        i = argv.index("--updates-per-user"); upu = [float(x) for x in argv[i + 1].split(",")]; del argv[i:i + 2]
+    skip_direct = "--skip-direct" in argv
+    if skip_direct:
+        argv.remove("--skip-direct")
     sys.argv = [sys.argv[0]] + argv
     a = bench.parse()
-    a.quality_updates_per_user = upu
+    a.quality_updates_per_user = max(upu)
+    a.skip_direct_quality = skip_direct
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     n_dev = torch.cuda.device_count()
@@ -41,7 +45,8 @@ def main():
         dist.init_process_group("gloo" if shared else "nccl", **({} if shared else {"device_id": dev}))
     from fps_b200.models.mf.device import DeviceOnlineMF, ERR_PLAIN
 
-    out = bench.quality_gate(a, world, rank, dev, shared, DeviceOnlineMF, ERR_PLAIN, sync_list=sync)
+    out = bench.quality_gate(a, world, rank, dev, shared, DeviceOnlineMF, ERR_PLAIN, sync_list=sync,
+                             checkpoints=upu)
     if rank == 0:
         out.update(n_workers=world, users=a.users, items=a.items, factors=a.factors, batch=a.batch, shared_gpu=shared)
         print(json.dumps(out), flush=True)

@@ -62,8 +62,10 @@ class DeviceOnlineMF:
         self.step_no = 0
         self.kernel = kernel
         # pull limiter (WL:196-250) = device credit counter [credits, stalls] consumed inside the fused kernel
+        # (a warp takes its credits all at once, so limits below one warp's worth of pulls fall back to the
+        # static form of the limiter: a capped grid)
         self.credits = (torch.tensor([self.pull_limit, 0], dtype=torch.int32, device=self.cuda_device)
-                        if self.pull_limit > 0 and os.environ.get("FPS_STATIC_LIMITER", "0") != "1" else None)
+                        if self.pull_limit >= 32 and os.environ.get("FPS_STATIC_LIMITER", "0") != "1" else None)
         self.output_ring = output_ring     # E5: per-update (user, vector) output stream (runtime/output_ring.py)
         with torch.cuda.device(self.device):
             # parameter server: item vectors, sharded item % psParallelism

@@ -58,19 +58,20 @@ extern "C" int fps_init_rows(float* rows, long long n_rows, int dim, int stride,
 // may still be issued; a lane-group takes one credit before it touches the owner's memory and returns
 // it when the answer has been consumed (stored), so at most `pullLimit` row pulls are un-answered at any
 // time whatever the grid size.  `credits[1]` counts the stalls (acquisitions that had to wait).
-__device__ __forceinline__ void fps_credit_acquire(int* credits) {
+__device__ __forceinline__ void fps_credit_acquire(int* credits, int n = 1) {
   bool stalled = false;
   unsigned ns = 256;
   while (true) {
-    // look before taking: waiters poll with a plain load and back off exponentially, so the counter's
-    // atomic unit stays available for the releases that make progress possible
-    if (*reinterpret_cast<volatile int*>(credits) > 0) {
-      if (atomicSub(credits, 1) > 0) break;
-      atomicAdd(credits, 1);
+    // compare-and-swap on a positive value only: the counter never goes negative, so waiters cannot hold it
+    // down (a sub-then-add-back scheme livelocks once thousands of lane-groups retry at the same time);
+    // waiters poll with a plain load and back off exponentially
+    const int cur = *reinterpret_cast<volatile int*>(credits);
+    if (cur >= n && atomicCAS(credits, cur, cur - n) == cur) break;
+    if (cur < n) {
+      stalled = true;
+      __nanosleep(ns);
+      if (ns < 8192) ns <<= 1;
     }
-    stalled = true;
-    __nanosleep(ns);
-    if (ns < 8192) ns <<= 1;
   }
   if (stalled) atomicAdd(credits + 1, 1);
 }
@@ -93,7 +94,6 @@ __device__ __forceinline__ void fps_credit_acquire(int* credits) {
 template <typename IdT, int LPR, int VPL, int R, int MINB, int FMT, int HINT = 0, int EMIT = 0, int LIMIT = 0>
 __global__ void __launch_bounds__(256, MINB)
     fps_mf_sgd_fused_kernel(const __grid_constant__ MfArgs a) {
-  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) & ~(LPR - 1)));
   unsigned long long pol_user = 0, pol_item = 0;
   if (HINT) {
     pol_user = fps_policy_evict_first();
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256, MINB)
     float rt[R];
     bool ok[R];
     long long uid[R];
+    int ncred[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const long long idx = base + (long long)r * n_groups + group;
@@ -160,9 +161,13 @@ __global__ void __launch_bounds__(256, MINB)
         }
       }
       uid[r] = (long long)user;
-      if (LIMIT) {   // take a pull credit before touching the owner; returned once the push is issued
-        if (lane == 0 && ok[r]) fps_credit_acquire(a.credits);
-        __syncwarp(gmask);
+      if (LIMIT) {
+        // One credit per pull, taken for the whole warp at once (all or nothing): the lane-groups of a warp
+        // meet again in the full-warp shuffles below, so a group must never hold a credit while a
+        // warp-mate waits for one.  Returned once the pushes are issued.
+        ncred[r] = __popc(__ballot_sync(0xffffffffu, ok[r] && lane == 0));
+        if ((threadIdx.x & 31) == 0 && ncred[r] > 0) fps_credit_acquire(a.credits, ncred[r]);
+        __syncwarp();
       }
       up[r] = a.user_sharded ? fps_row_t<IdT>(a.user_tab, user)
                              : a.user_table + fps_user_slot<IdT>(user, a.user_div, a.user_shift) * (size_t)stride;
@@ -199,8 +204,8 @@ __global__ void __launch_bounds__(256, MINB)
                                           : rt[r] - 1.f / (1.f + __expf(-d));
       const float g = a.lr * e;
       if (LIMIT) {
-        __syncwarp(gmask);                          // every lane holds its part of the answer
-        if (lane == 0 && ok[r]) atomicAdd(a.credits, 1);
+        __syncwarp();                               // every lane holds its part of the answer
+        if ((threadIdx.x & 31) == 0 && ncred[r] > 0) atomicAdd(a.credits, ncred[r]);
       }
       if (ok[r]) {
         if (!(fabsf(g) <= 3.0e38f)) bad = true;  // NaN/Inf guard (Vector.scala:78-80)

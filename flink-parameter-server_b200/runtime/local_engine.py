@@ -190,12 +190,12 @@ class LocalEngine:
 
         def worker_loop(i: int) -> None:
             logic, recv, client = w_logic[i], w_recv[i], clients[i]
-            inbox_get, on_answer_msg, done = w_inbox[i].get, recv.onPullAnswerRecv, act.done
 
             def on_answer(a: PullAnswer) -> None:
                 logic.onPullRecv(a.paramId, a.param, client)
 
-            try:
+            try:      # everything that can raise is inside: a dead thread must fail the job, not hang it
+                inbox_get, on_answer_msg, done = w_inbox[i].get, recv.onPullAnswerRecv, act.done
                 if self.call_worker_open:
                     logic.open()
                 on_recv = logic.onRecv          # bound after open(): a logic may rebind its callbacks there
@@ -215,7 +215,6 @@ class LocalEngine:
 
         def ps_loop(j: int) -> None:
             logic, recv, server = p_logic[j], p_recv[j], servers[j]
-            inbox_get, on_msg, done = ps_inbox[j].get, recv.onWorkerMsg, act.done
 
             def on_pull(id, widx) -> None:
                 logic.onPullRecv(id, widx, server)
@@ -227,6 +226,7 @@ class LocalEngine:
             # batches: drain whatever has queued up, decode it, then one flush() = a few kernels
             inbox = ps_inbox[j]
             try:
+                inbox_get, on_msg, done = ps_inbox[j].get, recv.onWorkerMsg, act.done
                 logic.open({}, RuntimeContext(j, self.psP))
                 flush = getattr(logic, "flush", None)
                 stop = False

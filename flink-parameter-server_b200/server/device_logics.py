@@ -209,20 +209,70 @@ class DeviceStoreLogic(LooseParameterServerLogic):
 
     # -- lifecycle ------------------------------------------------------------------------------
     def open(self, parameters, runtimeContext: RuntimeContext):
+        import os
         import torch
 
-        if not torch.cuda.is_available():
-            raise RuntimeError('backend="device" needs a CUDA device; use backend="local" on CPU')
         idx = runtimeContext.getIndexOfThisSubtask()
         self.shard, self.n_shards = idx, runtimeContext.getNumberOfParallelSubtasks()
-        self.device = torch.device("cuda", idx % torch.cuda.device_count())
-        self.stream = torch.cuda.Stream(device=self.device)
+        # FPS_DEVICE_STORE_EMULATE=1: the same store logic over host tensors and torch index ops -- the
+        # "fake backend" used by the CPU test-suite to exercise the engine path without a GPU
+        self.emulate = os.environ.get("FPS_DEVICE_STORE_EMULATE", "0") == "1"
+        if self.emulate:
+            self.device, self.stream = torch.device("cpu"), None
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError('backend="device" needs a CUDA device; use backend="local" on CPU')
+            self.device = torch.device("cuda", idx % torch.cuda.device_count())
+            self.stream = torch.cuda.Stream(device=self.device)
         if self.kind == "range_close":
             n, fc = self.n_shards, int(self.featureCount)
             div = int(math.ceil(fc / n))
             mod = fc - (n - 1) * div
             self.range_size = max(mod if (mod != 0 and idx + 1 == n) else div, 0)
             self.range_start = idx * div
+
+    # ---- the five device operations (kernels on CUDA, torch index ops when emulating) -------------------
+    def _ctx(self):
+        import contextlib
+        import torch
+
+        if self.emulate:
+            return contextlib.nullcontext()
+        stack = contextlib.ExitStack()
+        stack.enter_context(torch.cuda.device(self.device))
+        stack.enter_context(torch.cuda.stream(self.stream))
+        return stack
+
+    def _k_gather(self, ids, out):
+        if self.emulate:
+            out.copy_(self.rows[ids, : out.shape[1]])
+        else:
+            from ..ops import native
+            native.pull_gather(self.table_c, ids, out)
+
+    def _k_assign(self, ids, vals):
+        if self.emulate:
+            self.rows[ids, : vals.shape[1]] = vals
+        else:
+            from ..ops import native
+            native.push_assign(self.table_c, ids, vals)
+
+    def _k_add(self, ids, d, fetch: bool):
+        if self.emulate:
+            if not fetch:
+                self.rows.index_add_(0, ids, torch_pad(d, self.rows.shape[1]))
+                return None
+            out = []
+            for i, row in zip(ids.tolist(), d):      # returning adds: every push sees its own prefix sum
+                self.rows[i, : d.shape[1]] += row
+                out.append(self.rows[i, : self.codec.dim].clone())
+            import torch
+            return torch.stack(out)
+        from ..ops import native
+        if fetch:
+            return native.push_add_fetch(self.table_c, ids, d)
+        native.push_add(self.table_c, ids, d)
+        return None
 
     def _alloc(self, min_rows: int) -> None:
         import torch
@@ -235,12 +285,12 @@ class DeviceStoreLogic(LooseParameterServerLogic):
             cap *= 2
         if self.rows is not None and cap == self.rows.shape[0]:
             return
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+        with self._ctx():
             new = torch.zeros((cap, stride), dtype=torch.float32, device=self.device)
             if self.rows is not None:
                 new[: self.rows.shape[0]] = self.rows
             self.rows = new
-            self.table_c = native.local_table(self.rows, dim)
+            self.table_c = None if self.emulate else native.local_table(self.rows, dim)
 
     def _slot_of(self, id, create: bool) -> Tuple[int, bool]:
         s = self.slots.get(id)
@@ -308,20 +358,20 @@ class DeviceStoreLogic(LooseParameterServerLogic):
         if not slots:
             return
         self._alloc(max(slots) + 1)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+        with self._ctx():
             ids = torch.tensor(slots, dtype=torch.int64).to(self.device, non_blocking=True)
             vals = torch.from_numpy(np.stack(values).astype(np.float32)).to(self.device, non_blocking=True)
-            native.push_assign(self.table_c, ids, vals.contiguous())
+            self._k_assign(ids, vals.contiguous())
         self.stats["kernels"] += 1
 
     def _read_rows(self, slots: List[int]) -> np.ndarray:
         import torch
         from ..ops import native
 
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+        with self._ctx():
             ids = torch.tensor(slots, dtype=torch.int64).to(self.device, non_blocking=True)
             out = torch.empty((len(slots), self.codec.dim), dtype=torch.float32, device=self.device)
-            native.pull_gather(self.table_c, ids, out)
+            self._k_gather(ids, out)
             host = out.cpu()               # stream-ordered D2H, synchronises this stream only
         self.stats["kernels"] += 1
         return host.numpy()
@@ -413,26 +463,23 @@ class DeviceStoreLogic(LooseParameterServerLogic):
         outputs: List[Tuple[Any, Any]] = list(fresh_out) if emit else []
         for op, items in dev_ops.items():
             slots = [s for (s, _, _) in items]
-            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            with self._ctx():
                 ids = torch.tensor(slots, dtype=torch.int64).to(self.device, non_blocking=True)
                 d = torch.from_numpy(np.stack([x for (_, _, x) in items]).astype(np.float32)).to(
                     self.device, non_blocking=True).contiguous()
                 if op == OP_ADD:
-                    if emit:
-                        new = native.push_add_fetch(self.table_c, ids, d).cpu().numpy()
-                    else:
-                        native.push_add(self.table_c, ids, d)
-                        new = None
+                    new = self._k_add(ids, d, fetch=emit)
+                    new = new.cpu().numpy() if new is not None else None
                 else:
                     if op == OP_ASSIGN:
-                        native.push_assign(self.table_c, ids, d)
+                        self._k_assign(ids, d)
                         new_t = d
                     else:
                         cur = torch.empty((len(slots), self.codec.dim), dtype=torch.float32, device=self.device)
-                        native.pull_gather(self.table_c, ids, cur)
+                        self._k_gather(ids, cur)
                         new_t = torch.maximum(cur, d[:, : self.codec.dim]) if op == OP_MAX else \
                             torch.minimum(cur, d[:, : self.codec.dim])
-                        native.push_assign(self.table_c, ids, new_t.contiguous())
+                        self._k_assign(ids, new_t.contiguous())
                     new = new_t.cpu().numpy() if emit else None
             self.stats["kernels"] += 1
             if emit:
@@ -473,6 +520,12 @@ class DeviceStoreLogic(LooseParameterServerLogic):
         locked, q = self.locks.get(id, (False, deque()))
         val = self.codec.decode(self._read_rows([self.slots[id]])[0])
         return locked, val, list(q)
+
+
+def torch_pad(d, width: int):
+    import torch
+
+    return d if d.shape[1] == width else torch.nn.functional.pad(d, (0, width - d.shape[1]))
 
 
 def to_device_logic(psLogic):

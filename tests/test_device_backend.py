@@ -40,6 +40,19 @@ def test_update_classification_and_codec():
     assert to_device_logic(object()) is None
 
 
+def test_device_store_engine_path_on_the_cpu_emulation(monkeypatch):
+    """The same jobs with the five device operations emulated by torch index ops on host tensors
+    (``FPS_DEVICE_STORE_EMULATE=1``): the batching / ordering / store logic is covered by the CPU suite."""
+    monkeypatch.setenv("FPS_DEVICE_STORE_EMULATE", "1")
+    for job in (test_model_load_i_times_10_plus_3_on_device_stores,
+                test_word_count_string_ids_param_init_update_on_device, test_word_count_loose_types_on_device,
+                test_model_load_string_ids_custom_partitioner_on_device,
+                test_vector_params_and_host_fallback_update_match_the_host_engine, test_range_store_on_device):
+        job()
+    for cls, dup in ((LockPSLogicA, True), (LockPSLogicB, False)):
+        test_lock_stores_on_device(cls, dup)
+
+
 # ---- device --------------------------------------------------------------------------------------------
 gpu = pytest.mark.gpu
 
@@ -66,7 +79,8 @@ def test_model_load_i_times_10_plus_3_on_device_stores():
     assert sorted(out.ps_outputs()) == [(i, i * 10 + 3) for i in range(num)]
     stores = [lg.inner for lg in out.engine.ps_logics]
     assert all(s.is_device_store and s.stats["host_updates"] == 0 for s in stores)     # REDG path, not host RMW
-    assert sum(s.stats["pushes"] for s in stores) >= 3 * num and all(s.rows.is_cuda for s in stores)
+    assert sum(s.stats["pushes"] for s in stores) >= 3 * num
+    assert all(s.rows.is_cuda or s.emulate for s in stores)
 
 
 class WordPuller(WorkerLogic):
@@ -177,8 +191,8 @@ def test_vector_params_and_host_fallback_update_match_the_host_engine():
 def test_range_store_on_device():
     data = list(range(0, 30, 3)) * 2
     out = transform(data, PullThenPushOne(), RangePSLogicWithClose(30, lambda i: i, operator.add),
-                    lambda m: min(m.paramId // 10, 2), lambda m: m.workerPartitionIndex, 2, 3, WAIT,
-                    backend="device")
+                    lambda m: min(m.paramId // 10, 2), lambda m: m.workerPartitionIndex, 2, 3,
+                    iterationWaitTime=WAIT, backend="device")
     assert sorted(out.ps_outputs()) == [(i, i + 2) for i in range(0, 30, 3)]
 
 

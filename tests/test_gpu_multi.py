@@ -15,7 +15,7 @@ from tests.mp_util import REPO, launch_cmd
 pytestmark = pytest.mark.gpu
 
 
-def _run(script: str, world: int, port: int, ok: str, timeout: int = 900):
+def _run(script: str, world: int, port: int, ok: str, timeout: int = 420):
     env = dict(os.environ)
     if torch.cuda.device_count() < world:
         env["FPS_SHARE_GPU"] = "1"
