@@ -48,11 +48,15 @@ struct Entry {                 // followed by `stride` floats of payload
 };
 
 struct RingSet {               // one direction of one rank's rings, as seen by one side
-  unsigned char* base[RING_MAX_PEERS];   // ring base address per peer (header + entries)
+  unsigned char* const* base;  // device table of ring base addresses (header + entries), [n_peers * lanes]:
+                               //   ring of (peer p, lane l) = base[p * lanes + l]
   int n_peers;
+  int lanes;                   // parallel rings per (worker, shard) pair; a key always uses lane
+                               //   slot(id) % lanes, so FIFO order per key and pair is preserved
   int capacity;                // entries per ring (power of two)
   int stride;                  // payload floats
   int entry_bytes;             // sizeof(Entry) + 4 * stride, multiple of 16
+  int pad_;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -74,7 +78,8 @@ __device__ __forceinline__ float* entry_payload(Entry* e) {
   return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(e) + sizeof(Entry));
 }
 
-// Warp-cooperative enqueue (single producer per ring).  Returns false on spin-limit.
+// Warp-cooperative enqueue (single producer per ring).  `peer` is the RING INDEX (peer * lanes + lane).
+// Returns false on spin-limit.
 __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long id, unsigned tag,
                          const float* payload, int lane, int* err) {
   RingHdr* h = ring_hdr(r, peer);
@@ -155,18 +160,22 @@ __device__ void apply_update(const ServerArgs& a, float* row, const float* delta
   __threadfence();
 }
 
-__device__ bool answer(const ServerArgs& a, int worker, long long id, unsigned tag, const float* row,
-                       int lane) {
-  const bool ok = ring_put(a.resp, worker, OP_PULL, a.self, id, tag, row, lane, a.err);
+__device__ bool answer(const ServerArgs& a, int worker, int ring_lane, long long id, unsigned tag,
+                       const float* row, int lane) {
+  const bool ok = ring_put(a.resp, worker * a.resp.lanes + ring_lane, OP_PULL, a.self, id, tag, row, lane, a.err);
   if (ok && lane == 0) atomicAdd(a.counters + 2, 1ull);
   return ok;
 }
 
-__global__ void __launch_bounds__(32 * RING_MAX_PEERS)
+// One warp per request ring; the rings of one shard are spread over as many CTAs as needed (8 warps each),
+// so a shard with W workers x L lanes is served by W * L warps in parallel.
+#define SERVER_WARPS 8
+__global__ void __launch_bounds__(32 * SERVER_WARPS)
     fps_server_loop_kernel(const __grid_constant__ ServerArgs a) {
-  const int w = threadIdx.x >> 5;  // this warp serves the ring of worker w
+  const int w = blockIdx.x * SERVER_WARPS + (threadIdx.x >> 5);  // this warp serves request ring w
   const int lane = threadIdx.x & 31;
-  if (w >= a.req.n_peers) return;
+  if (w >= a.req.n_peers * a.req.lanes) return;
+  const int ring_lane = w % a.req.lanes;
   RingHdr* h = ring_hdr(a.req, w);
   unsigned long long tail = h->tail;
   unsigned idle = 0;
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(32 * RING_MAX_PEERS)
     if (a.lock_mode == LOCK_NONE) {
       if (op == OP_PULL) {
         if (lane == 0 && a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
-        if (!answer(a, worker, id, tag, row, lane)) return;
+        if (!answer(a, worker, ring_lane, id, tag, row, lane)) return;
         if (lane == 0) atomicAdd(a.counters + 0, 1ull);
       } else {
         apply_update(a, row, entry_payload(e), lane);
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(32 * RING_MAX_PEERS)
       granted = __shfl_sync(0xffffffffu, granted, 0);
       if (op == OP_PULL) {
         if (lane == 0) { __threadfence(); atomicExch(a.lock_mutex + slot, 0); }
-        if (granted && !answer(a, worker, id, tag, row, lane)) return;
+        if (granted && !answer(a, worker, ring_lane, id, tag, row, lane)) return;
         if (lane == 0) atomicAdd(a.counters + 0, 1ull);
       } else {
         apply_update(a, row, entry_payload(e), lane);
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(32 * RING_MAX_PEERS)
         }
         hand_worker = __shfl_sync(0xffffffffu, hand_worker, 0);
         hand_tag = __shfl_sync(0xffffffffu, hand_tag, 0);
-        if (hand_worker >= 0 && !answer(a, hand_worker, id, hand_tag, row, lane)) return;
+        if (hand_worker >= 0 && !answer(a, hand_worker, ring_lane, id, hand_tag, row, lane)) return;
       }
     }
     ++tail;
@@ -268,7 +277,8 @@ __global__ void __launch_bounds__(32 * RING_MAX_PEERS)
 }
 
 extern "C" int fps_server_loop_launch(const ServerArgs* a, cudaStream_t stream) {
-  fps_server_loop_kernel<<<1, 32 * a->req.n_peers, 0, stream>>>(*a);
+  const int rings = a->req.n_peers * a->req.lanes;
+  fps_server_loop_kernel<<<(rings + SERVER_WARPS - 1) / SERVER_WARPS, 32 * SERVER_WARPS, 0, stream>>>(*a);
   return (int)cudaGetLastError();
 }
 
@@ -293,17 +303,18 @@ struct ClientArgs {
   int self;           // worker index
 };
 
-__device__ __forceinline__ int owner_of(const ShardTable& t, long long id) {
+// request / response ring index of a key: (owner shard, slot % lanes)
+__device__ __forceinline__ int ring_of(const ShardTable& t, int lanes, long long id) {
   int owner; long long slot;
   fps_locate(t, id, owner, slot);
-  return owner;
+  return owner * lanes + (int)(slot % lanes);
 }
 
 __device__ bool issue_pull(const ClientArgs& a, long long id, int lane) {
   unsigned tag = 0;
   if (lane == 0) { tag = a.st->next_tag++; }
   tag = __shfl_sync(0xffffffffu, tag, 0);
-  const bool ok = ring_put(a.req, owner_of(a.tab, id), OP_PULL, a.self, id, tag, nullptr, lane, &a.st->err);
+  const bool ok = ring_put(a.req, ring_of(a.tab, a.req.lanes, id), OP_PULL, a.self, id, tag, nullptr, lane, &a.st->err);
   if (ok && lane == 0) a.st->issued++;
   return ok;
 }
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(32)
   for (int i = 0; i < n; ++i) {
     const long long id = ids[i];
     if (op == OP_PUSH) {
-      if (!ring_put(a.req, owner_of(a.tab, id), OP_PUSH, a.self, id, 0u,
+      if (!ring_put(a.req, ring_of(a.tab, a.req.lanes, id), OP_PUSH, a.self, id, 0u,
                     deltas + (size_t)i * a.req.stride, lane, &a.st->err))
         return;
       continue;
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(32)
                               float* __restrict__ out_vals, int max_n, int* __restrict__ n_out) {
   const int lane = threadIdx.x;
   int got = 0;
-  for (int s = 0; s < a.resp.n_peers && got < max_n; ++s) {
+  for (int s = 0; s < a.resp.n_peers * a.resp.lanes && got < max_n; ++s) {
     RingHdr* h = ring_hdr(a.resp, s);
     unsigned long long tail = h->tail;
     while (got < max_n) {
@@ -378,6 +389,119 @@ extern "C" int fps_client_collect(const ClientArgs* a, long long* out_ids, float
   fps_client_collect_kernel<<<1, 32, 0, stream>>>(*a, out_ids, out_vals, max_n, n_out);
   return (int)cudaGetLastError();
 }
+// ============================================================================================
+// throughput path: batched transactions through the message tier
+// ============================================================================================
+// A worker hands the kernel a whole micro-batch of keys, pre-sorted by ring (owner shard, lane).  One warp
+// per ring is BOTH the single producer of the request ring and the single consumer of the response ring:
+//   * pulls are issued in order under the worker's device credit counter (pullLimit, WL:196-250) -- the
+//     keys that have not been issued yet ARE the FIFO spill queue of the limiter;
+//   * every answer is copied to out_vals[message], releases its credit and (mode PULL_PUSH) immediately
+//     triggers push(id, deltas[message]) -- the onPullRecv -> ps.push pattern of every reference worker
+//     (e.g. PSOnlineMatrixFactorizationWorker.scala:42-55), which is also what releases a LockPSLogic lock;
+//   * mode PUSH_ONLY streams pushes (non-commutative `assign` / max / min updates are applied by the
+//     server warps in ring order).
+// No launch per drain: the kernel lives until its messages are sent and all its pulls are answered.
+// Deadlock freedom: a ring never has more pulls outstanding than its response ring holds, so a server
+// warp never blocks on this worker's response ring and therefore always drains the request ring.
+enum TxnMode : int { TXN_PULL_PUSH = 0, TXN_PULL_ONLY = 1, TXN_PUSH_ONLY = 2 };
+struct TxnArgs {
+  RingSet req;            // request rings of every (shard, lane) for me (peer memory)
+  RingSet resp;           // my response rings, same indexing (local memory)
+  const long long* ids;   // [n] keys sorted by ring index
+  const float* deltas;    // [n, stride] (modes with a push)
+  const int* seg;         // [rings + 1] segment offsets into ids
+  float* out_vals;        // [n, stride] answers, by message (pull modes)
+  int* credits;           // worker-wide credit counter: [credits, stalls]
+  int* err;
+  unsigned long long* counters;  // [0] pulls sent, [1] pushes sent, [2] answers consumed
+  int self;
+  int mode;
+};
+
+#define TXN_WARPS 8
+__global__ void __launch_bounds__(32 * TXN_WARPS)
+    fps_client_txn_kernel(const __grid_constant__ TxnArgs a) {
+  const int r = blockIdx.x * TXN_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n_rings = a.req.n_peers * a.req.lanes;
+  if (r >= n_rings) return;
+  int pos = a.seg[r];
+  const int end = a.seg[r + 1];
+  if (pos == end) return;
+  RingHdr* hr = ring_hdr(a.resp, r);
+  unsigned long long rtail = hr->tail;
+  int outstanding = 0;
+  const int max_out = a.resp.capacity;
+  const int stride = a.req.stride;
+  unsigned long long n_pull = 0, n_push = 0, n_ans = 0;
+  unsigned idle = 0;
+  while (pos < end || outstanding > 0) {
+    bool progressed = false;
+    // ---- consume answers ------------------------------------------------------------------------------------
+    if (outstanding > 0) {
+      unsigned long long rhead = 0;
+      if (lane == 0) rhead = ld_acquire_sys(&hr->head);
+      rhead = __shfl_sync(0xffffffffu, rhead, 0);           // one observation for the whole warp
+      while (rtail != rhead) {
+        Entry* e = ring_entry(a.resp, r, rtail);
+        const unsigned msg = e->tag;
+        const long long id = e->id;
+        const float* src = entry_payload(e);
+        for (int q = lane; q < stride; q += 32) a.out_vals[(size_t)msg * stride + q] = src[q];
+        __syncwarp();
+        ++rtail;
+        if (lane == 0) st_release_sys(&hr->tail, rtail);
+        --outstanding; ++n_ans;
+        if (a.mode == TXN_PULL_PUSH) {
+          if (!ring_put(a.req, r, OP_PUSH, a.self, id, msg, a.deltas + (size_t)msg * stride, lane, a.err)) return;
+          ++n_push;
+        }
+        if (lane == 0) atomicAdd(a.credits, 1);            // onPullRecv done: release the credit
+        progressed = true;
+      }
+    }
+    // ---- issue the next message -------------------------------------------------------------------------------
+    if (pos < end) {
+      if (a.mode == TXN_PUSH_ONLY) {
+        if (!ring_put(a.req, r, OP_PUSH, a.self, a.ids[pos], (unsigned)pos, a.deltas + (size_t)pos * stride, lane, a.err))
+          return;
+        ++pos; ++n_push;
+        progressed = true;
+      } else if (outstanding < max_out) {
+        int got = 0;
+        if (lane == 0) {                                    // one non-blocking attempt on the credit counter
+          const int cur = *reinterpret_cast<volatile int*>(a.credits);
+          if (cur > 0 && atomicCAS(a.credits, cur, cur - 1) == cur) got = 1;
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got) {
+          if (!ring_put(a.req, r, OP_PULL, a.self, a.ids[pos], (unsigned)pos, nullptr, lane, a.err)) return;
+          ++pos; ++outstanding; ++n_pull;
+          progressed = true;
+        }
+      }
+    }
+    if (progressed) {
+      idle = 0;
+    } else {
+      if (++idle > FPS_SPIN_LIMIT) { if (lane == 0) atomicExch(a.err, ERR_SPIN); return; }
+      if (idle > 16) __nanosleep(128);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, n_pull);
+    atomicAdd(a.counters + 1, n_push);
+    atomicAdd(a.counters + 2, n_ans);
+  }
+}
+
+extern "C" int fps_client_txn(const TxnArgs* a, cudaStream_t stream) {
+  const int rings = a->req.n_peers * a->req.lanes;
+  fps_client_txn_kernel<<<(rings + TXN_WARPS - 1) / TXN_WARPS, 32 * TXN_WARPS, 0, stream>>>(*a);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int fps_ring_entry_bytes(int stride) {
   int b = (int)sizeof(Entry) + 4 * stride;
   return (b + 15) / 16 * 16;
@@ -394,5 +518,6 @@ extern "C" int fps_rings_preload() {
   cudaError_t e = cudaFuncGetAttributes(&fa, fps_server_loop_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fps_client_issue_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fps_client_collect_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fps_client_txn_kernel);
   return (int)e;
 }

@@ -33,8 +33,17 @@ ERRORS = {1: "spin limit exceeded (peer not draining its ring)", 2: "push to an 
 
 
 class RingSetC(C.Structure):
-    _fields_ = [("base", C.c_void_p * RING_MAX_PEERS), ("n_peers", C.c_int), ("capacity", C.c_int),
-                ("stride", C.c_int), ("entry_bytes", C.c_int)]
+    _fields_ = [("base", C.c_void_p), ("n_peers", C.c_int), ("lanes", C.c_int), ("capacity", C.c_int),
+                ("stride", C.c_int), ("entry_bytes", C.c_int), ("pad_", C.c_int)]
+
+
+class TxnArgsC(C.Structure):
+    _fields_ = [("req", RingSetC), ("resp", RingSetC), ("ids", C.c_void_p), ("deltas", C.c_void_p),
+                ("seg", C.c_void_p), ("out_vals", C.c_void_p), ("credits", C.c_void_p), ("err", C.c_void_p),
+                ("counters", C.c_void_p), ("self", C.c_int), ("mode", C.c_int)]
+
+
+TXN_PULL_PUSH, TXN_PULL_ONLY, TXN_PUSH_ONLY = 0, 1, 2
 
 
 class ServerArgsC(C.Structure):
@@ -52,38 +61,51 @@ class ClientArgsC(C.Structure):
 
 
 class RingFabric:
-    """Request + response rings of every (worker, shard) pair; rank r is worker r and shard r."""
+    """Request + response rings of every (worker, shard) pair; rank r is worker r and shard r.
 
-    def __init__(self, stride: int, capacity: int = 1024, group=None, device: Optional[int] = None):
+    ``lanes`` parallel rings per pair (a key always travels on lane ``slot(id) % lanes``, which keeps the
+    per-key FIFO order the reference's answer queues rely on): the persistent server serves every ring
+    with its own warp, spread over as many CTAs as needed -- the throughput knob of the message tier."""
+
+    def __init__(self, stride: int, capacity: int = 1024, group=None, device: Optional[int] = None,
+                 lanes: int = 1):
         assert capacity & (capacity - 1) == 0, "ring capacity must be a power of two"
         ready = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if ready else 1
         self.rank = dist.get_rank(group) if ready else 0
-        self.stride, self.capacity = int(stride), int(capacity)
+        self.stride, self.capacity, self.lanes = int(stride), int(capacity), max(1, int(lanes))
         lib = native.lib()
         self.entry_bytes = lib.fps_ring_entry_bytes(self.stride)
         self.ring_bytes = (lib.fps_ring_bytes(self.capacity, self.stride) + 255) // 256 * 256
-        self.heap = SymmetricHeap(2 * self.world * self.ring_bytes, group=group, device=device)
+        # per rank: request rings [worker][lane], then response rings [shard][lane]
+        self.heap = SymmetricHeap(2 * self.world * self.lanes * self.ring_bytes, group=group, device=device)
+        self._tables = []        # device pointer tables (kept alive)
 
     def _set(self, bases) -> RingSetC:
+        dev = torch.device("cuda", self.heap.device)
+        tab = torch.tensor(list(bases), dtype=torch.int64, device=dev)
+        self._tables.append(tab)
         r = RingSetC()
-        for i, b in enumerate(bases):
-            r.base[i] = b
-        r.n_peers, r.capacity, r.stride, r.entry_bytes = self.world, self.capacity, self.stride, self.entry_bytes
+        r.base = tab.data_ptr()
+        r.n_peers, r.lanes, r.capacity = self.world, self.lanes, self.capacity
+        r.stride, r.entry_bytes = self.stride, self.entry_bytes
         return r
+
+    def _off(self, block: int, peer: int, lane: int) -> int:
+        return ((block * self.world + peer) * self.lanes + lane) * self.ring_bytes
 
     # server view: my request rings (local), the workers' response rings for me (peer)
     def server_sets(self) -> Tuple[RingSetC, RingSetC]:
-        W, me, rb = self.world, self.rank, self.ring_bytes
-        req = self._set([self.heap.local_ptr + w * rb for w in range(W)])
-        resp = self._set([self.heap.peer_ptrs[w] + (W + me) * rb for w in range(W)])
+        W, L, me = self.world, self.lanes, self.rank
+        req = self._set([self.heap.local_ptr + self._off(0, w, l) for w in range(W) for l in range(L)])
+        resp = self._set([self.heap.peer_ptrs[w] + self._off(1, me, l) for w in range(W) for l in range(L)])
         return req, resp
 
     # client view: every shard's request ring for me (peer), my response rings (local)
     def client_sets(self) -> Tuple[RingSetC, RingSetC]:
-        W, me, rb = self.world, self.rank, self.ring_bytes
-        req = self._set([self.heap.peer_ptrs[s] + me * rb for s in range(W)])
-        resp = self._set([self.heap.local_ptr + (W + s) * rb for s in range(W)])
+        W, L, me = self.world, self.lanes, self.rank
+        req = self._set([self.heap.peer_ptrs[s] + self._off(0, me, l) for s in range(W) for l in range(L)])
+        resp = self._set([self.heap.local_ptr + self._off(1, s, l) for s in range(W) for l in range(L)])
         return req, resp
 
     def close(self):
@@ -175,6 +197,10 @@ class DeviceRingClient:
                  spill_capacity: int = 1 << 16):
         dev = table.cuda_device
         self.dev, self.stride = dev, rings.stride
+        self.table, self.rings = table, rings
+        self.txn_credits = torch.tensor([pull_limit, 0], dtype=torch.int32, device=dev)
+        self.txn_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.txn_counters = torch.zeros(3, dtype=torch.int64, device=dev)
         self.state = torch.zeros(10, dtype=torch.int32, device=dev)
         self.state[0] = pull_limit
         self.state[1] = pull_limit
@@ -193,6 +219,17 @@ class DeviceRingClient:
             d[:, :1] = torch.ones(2, 1, device=dev)
             _ = torch.empty(4, dtype=torch.int64, device=dev)[:2].to("cpu")
             _ = self.state.to("cpu"); _ = self.n_out.to("cpu")
+            if rings.lanes >= 1:     # warm the torch kernels of the batched path (lazy loading, see start())
+                t = torch.arange(64, device=dev, dtype=torch.int64)
+                r_ = (t % 3) * 2 + (t // 3) % 2
+                o_ = torch.argsort(r_, stable=True)
+                sg = torch.zeros(8, dtype=torch.int32, device=dev)
+                sg[1:] = torch.cumsum(torch.bincount(r_, minlength=7), 0).to(torch.int32)
+                dd = torch.zeros((64, self.stride), dtype=torch.float32, device=dev)
+                dd[:, :1] = torch.ones(64, 1, device=dev)[o_]
+                oo = torch.empty_like(dd); oo[o_] = dd
+                _ = torch.clamp(t // 5, max=3); _ = t[o_].contiguous()
+                _ = self.txn_err.to("cpu"); _ = self.txn_counters.to("cpu"); _ = self.txn_credits.to("cpu")
         self.stream.synchronize()
         torch.cuda.current_stream().synchronize()
 
@@ -225,6 +262,66 @@ class DeviceRingClient:
             native._bump()
             n = int(self.n_out.to("cpu")[0])
         return ids[:n], vals[:n]
+
+    # ---- throughput path: a whole micro-batch through ONE persistent client kernel ------------------------
+    def _txn(self, ids: torch.Tensor, deltas: Optional[torch.Tensor], mode: int):
+        dev, stride = self.dev, self.stride
+        ids = ids.to(dev, torch.int64).contiguous()
+        n = ids.numel()
+        tab, L = self.table, self.rings.lanes
+        with torch.cuda.stream(self.stream):
+            if tab.mode == native.PART_HASH:
+                owner, slot = ids % tab.n_shards, ids // tab.n_shards
+            else:
+                owner = torch.clamp(ids // tab.div, max=tab.n_shards - 1)
+                slot = ids - owner * tab.div
+            ring = owner * L + slot % L
+            order = torch.argsort(ring, stable=True)          # per-key order is kept inside a ring
+            seg = torch.zeros(tab.n_shards * L + 1, dtype=torch.int32, device=dev)
+            seg[1:] = torch.cumsum(torch.bincount(ring, minlength=tab.n_shards * L), 0).to(torch.int32)
+            sid = ids[order].contiguous()
+            d = None
+            if deltas is not None:
+                d = torch.zeros((n, stride), dtype=torch.float32, device=dev)
+                d[:, : deltas.shape[1]] = deltas.to(dev)[order]
+            out = torch.zeros((n, stride), dtype=torch.float32, device=dev) if mode != TXN_PUSH_ONLY else None
+            a = TxnArgsC()
+            a.req, a.resp = self.args.req, self.args.resp
+            a.ids, a.seg = sid.data_ptr(), seg.data_ptr()
+            a.deltas = d.data_ptr() if d is not None else None
+            a.out_vals = out.data_ptr() if out is not None else None
+            a.credits, a.err, a.counters = self.txn_credits.data_ptr(), self.txn_err.data_ptr(), self.txn_counters.data_ptr()
+            a.self, a.mode = self.rings.rank, mode
+            native._check(native.lib().fps_client_txn(C.byref(a), C.c_void_p(self.stream.cuda_stream)), "client_txn")
+            native._bump()
+            res = None
+            if out is not None:
+                res = torch.empty_like(out)
+                res[order] = out
+        self._keep = (sid, seg, d, out)
+        return res
+
+    def transact(self, ids: torch.Tensor, deltas: torch.Tensor) -> torch.Tensor:
+        """For every key: pull, and on the answer push ``delta`` (``onPullRecv -> ps.push``), all inside one
+        persistent kernel under the device credit counter.  Returns the pulled values ``[n, stride]`` (a
+        future on the client stream: call :meth:`wait` before reading)."""
+        return self._txn(ids, deltas, TXN_PULL_PUSH)
+
+    def pull_all(self, ids: torch.Tensor) -> torch.Tensor:
+        return self._txn(ids, None, TXN_PULL_ONLY)
+
+    def push_all(self, ids: torch.Tensor, deltas: torch.Tensor) -> None:
+        self._txn(ids, deltas, TXN_PUSH_ONLY)
+
+    def wait(self) -> dict:
+        self.stream.synchronize()
+        with torch.cuda.stream(self.stream):
+            code = int(self.txn_err.to("cpu")[0])
+            c = self.txn_counters.to("cpu").tolist()
+            cr = self.txn_credits.to("cpu").tolist()
+        if code:
+            raise RuntimeError(f"device client: {ERRORS.get(code, code)}")
+        return {"pulls": c[0], "pushes": c[1], "answers": c[2], "credits": cr[0], "stalls": cr[1]}
 
     def counters(self) -> dict:
         with torch.cuda.stream(self.stream):

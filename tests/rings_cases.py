@@ -140,3 +140,71 @@ def test_transform_rings_runs_reference_style_worker_logic_against_device_server
     assert out.server_stats["pulls"] == 48 and out.server_stats["pushes"] == 48
     assert out.client_counters["issued"] == 48 and out.client_counters["credits"] == 8
     table.close()
+
+
+# ---- throughput path: multi-lane rings, multi-CTA server, one persistent client kernel per batch ----------------
+def _setup_mt(dim=8, n=4000, update="add", lock=None, limit=256, lanes=8, capacity=128):
+    from fps_b200.parallel.rings import DeviceMessageServer, DeviceRingClient, RingFabric
+    from fps_b200.store.sharded_table import ShardedTable
+
+    torch.cuda.set_device(0)
+    table = ShardedTable(n, dim, seed=9, init_range=(0.0, 1.0))
+    rings = RingFabric(table.stride, capacity=capacity, lanes=lanes)
+    server = DeviceMessageServer(table, rings, update=update, lock=lock)
+    client = DeviceRingClient(table, rings, pull_limit=limit)
+    server.start()
+    return table, rings, server, client
+
+
+def test_batched_pull_then_push_transactions_on_many_lanes():
+    table, rings, server, client = _setup_mt()
+    try:
+        ref = table.local[:, :8].clone()
+        g = torch.Generator().manual_seed(1)
+        ids = torch.randperm(4000, generator=g)[:3000]
+        deltas = torch.randn(3000, 8, generator=g)
+        vals = client.transact(ids, deltas)
+        st = client.wait()
+        assert st["pulls"] == 3000 and st["pushes"] == 3000 and st["answers"] == 3000
+        assert st["credits"] == 256                                   # every credit returned
+        torch.testing.assert_close(vals[:, :8].cpu(), ref[ids].cpu())  # unique keys: the value before the push
+        server.stop()
+        exp = ref.clone(); exp[ids.cuda()] += deltas.cuda()
+        torch.testing.assert_close(table.local[:, :8], exp)
+        assert server.stats() == {"pulls": 3000, "pushes": 3000, "answers": 3000}
+    finally:
+        server.stop(); rings.close(); table.close()
+
+
+def test_lock_a_serialises_read_modify_write_of_a_hot_key():
+    """20 keys x 200 transactions each (pull, then push +1 on the answer) under LockPSLogicA: the lock makes
+    every pull see a distinct committed value, so the answers of a key are exactly init, init+1, ..."""
+    table, rings, server, client = _setup_mt(lock="A", limit=512, lanes=4)
+    try:
+        ref = table.local[:, :8].clone()
+        ids = torch.arange(20).repeat_interleave(200)
+        ids = ids[torch.randperm(ids.numel(), generator=torch.Generator().manual_seed(2))]
+        vals = client.transact(ids, torch.ones(ids.numel(), 8))
+        client.wait()
+        server.stop()
+        for k in range(20):
+            seen = torch.sort(vals[ids == k, 0].cpu() - ref[k, 0].cpu()).values
+            torch.testing.assert_close(seen, torch.arange(200, dtype=torch.float32), rtol=0, atol=1e-3)
+        torch.testing.assert_close(table.local[:20, 0], ref[:20, 0] + 200)
+    finally:
+        server.stop(); rings.close(); table.close()
+
+
+def test_push_only_stream_applies_a_non_commutative_assign_in_key_order():
+    table, rings, server, client = _setup_mt(update="assign", lanes=8)
+    try:
+        ids = torch.arange(50).repeat(40)                      # 40 assignments per key, in stream order
+        vals = torch.arange(ids.numel(), dtype=torch.float32)[:, None].expand(-1, 8).contiguous()
+        client.push_all(ids, vals)
+        st = client.wait()
+        assert st["pushes"] == ids.numel()
+        server.stop()
+        last = torch.arange(50, dtype=torch.float32) + 39 * 50    # the LAST assignment of every key wins
+        torch.testing.assert_close(table.local[:50, 0].cpu(), last)
+    finally:
+        server.stop(); rings.close(); table.close()
