@@ -58,10 +58,10 @@ def parse():
     p.add_argument("--update-rule", default="parity", choices=["parity", "plain"],
                    help="parity: the reference's e = sigmoid(r - u.v) (SGDUpdater.scala:8; always positive, so "
                         "the squared error drifts up by design); plain: e = r - u.v (textbook SGD, loss falls)")
-    p.add_argument("--quality-updates-per-user", type=float, default=400.0,
+    p.add_argument("--quality-updates-per-user", type=float, default=1200.0,
                    help="convergence gate (outside the timed regions): total update budget = this x users, the "
                         "same synthetic low-rank stream trained by the replica mode, the direct one-sided mode "
-                        "and ONE worker alone; 0 disables")
+                        "and ONE worker alone, RMSE evaluated at 1/3 and at the full budget; 0 disables")
     p.add_argument("--quality-lr", type=float, default=0.05)
     p.add_argument("--quality-init", type=float, default=0.05)
     p.add_argument("--no-direct", action="store_true", help="skip the direct one-sided mode measurement (N > 1)")
@@ -366,7 +366,8 @@ def main():
     quality = None
     if a.impl == "fps_b200" and a.quality_updates_per_user > 0:
         try:
-            quality = quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN)
+            quality = quality_gate(a, world, rank, dev, shared_gpu, DeviceOnlineMF, ERR_PLAIN,
+                                   checkpoints=[a.quality_updates_per_user / 3, a.quality_updates_per_user])
         except Exception as exc:     # the headline line must be printed whatever happens here
             quality = {"error": f"{type(exc).__name__}: {exc}"}
         barrier()

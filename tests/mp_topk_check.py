@@ -71,7 +71,7 @@ def main():
         full.update(dict(p))
     target = full[java_string_hash("cat")]
     host = sorted(((median_of_means(v, target, 96, 6), k) for k, v in full.items()), reverse=True)[:3]
-    assert [k for _, k in got][:2] == [k for _, k in host][:2], (got, host)
+    assert {k for _, k in got[:2]} == {k for _, k in host[:2]}, (got, host)      # cat / dog tie at the top
     for (a, _), (b, _) in zip(got, host):
         assert abs(a - b) < 1e-3 * max(1.0, abs(b))
     sk.close()
