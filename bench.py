@@ -65,6 +65,8 @@ def parse():
     p.add_argument("--quality-lr", type=float, default=0.05)
     p.add_argument("--quality-init", type=float, default=0.05)
     p.add_argument("--no-direct", action="store_true", help="skip the direct one-sided mode measurement (N > 1)")
+    p.add_argument("--no-fp64", action="store_true",
+                   help="skip the fp64 row (the reference's precision: Array[Double] factors)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: reg = register-staged loads at full occupancy)")
     return p.parse_args()
@@ -360,6 +362,31 @@ def main():
                   "ms_per_step": d_ms / a.steps,
                   "note": "item_cache off: per-update one-sided pull (peer LDG.128) + push (REDG.ADD.F32x4) "
                           "over NVLink inside the fused kernel; link bound for remote rows"}
+    # ---- the reference's precision: fp64 tables and math (Vector.scala:8), direct one-sided mode -----------------
+    fp64 = None
+    if a.impl == "fps_b200" and not a.no_fp64:
+        from fps_b200.models.mf.device_f64 import DeviceOnlineMFf64
+
+        fm = DeviceOnlineMFf64(a.users, a.items, a.factors, learning_rate=a.lr, seed=1234,
+                               err_mode=ERR_SIGMOID if a.update_rule == "parity" else ERR_PLAIN)
+        for s in range(a.warmup):
+            fm.step(*devb[s % len(devb)])
+        barrier()
+        w0 = time.time()
+        e0.record()
+        for s in range(a.steps):
+            fm.step(*devb[(a.warmup + s) % len(devb)])
+        e1.record()
+        torch.cuda.synchronize()
+        f_ms = max_over_ranks(e0.elapsed_time(e1))
+        windows.append((w0, time.time()))
+        fm.check_finite()
+        barrier()
+        fm.close()
+        del fm
+        fp64 = {"value": a.steps * a.batch * world / (f_ms / 1e3), "unit": "updates/s", "ms_per_step": f_ms / a.steps,
+                "note": "fp64 tables and math like the reference (Array[Double]); 512-byte rows, "
+                        "ld.global.v2.f64 pulls + red.global.add.f64 pushes; direct one-sided mode at N > 1"}
     clocks = sampler.stop(windows) if rank == 0 else None
 
     # ---- convergence gate (outside every timed region) ---------------------------------------------
@@ -407,6 +434,7 @@ def main():
                                     if getattr(model, "replica", None) is not None else None),
                        "quality": quality},
             "value_direct": direct,
+            "value_fp64": fp64,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": e2e_ms_max / a.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

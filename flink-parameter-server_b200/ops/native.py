@@ -312,6 +312,45 @@ def mf_sgd_fused(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor
     _bump()
 
 
+def init_rows_f64(rows: torch.Tensor, dim: int, shard: int, num_shards: int, mode: int, div: int, seed: int,
+                  lo: float, hi: float) -> None:
+    """Philox init-by-id of fp64 rows ``[n, stride_doubles]`` (53-bit uniforms)."""
+    _req(rows, "rows", torch.float64)
+    _check(lib().fps_init_rows_f64(C.c_void_p(rows.data_ptr()), C.c_longlong(rows.shape[0]), int(dim),
+                                   int(rows.shape[1]), int(shard), int(num_shards), int(mode), C.c_longlong(div),
+                                   C.c_ulonglong(seed & (2**64 - 1)), C.c_double(lo), C.c_double(hi), _stream()),
+           "init_rows_f64")
+    _bump()
+
+
+def mf_sgd_fused_f64(users: torch.Tensor, items: Optional[torch.Tensor], ratings: Optional[torch.Tensor],
+                     user_table: torch.Tensor, user_div: int, item_tab: ShardTableC, lr: float,
+                     err_mode: int = 0, stats: Optional[torch.Tensor] = None,
+                     nan_flag: Optional[torch.Tensor] = None) -> None:
+    """fp64 fused pull + SGD + push (csrc/fps_mf_f64.cu): ``user_table`` is float64 ``[n, k_pad]``, the shards
+    of ``item_tab`` hold doubles (stride counted in 4-byte cells).  ``items=None``: packed64 records."""
+    _req(users, "users"); _req(user_table, "user_table", torch.float64)
+    packed = items is None
+    if not packed:
+        _req(items, "items"); _req(ratings, "ratings", torch.float32)
+    if user_table.shape[1] * 2 != item_tab.stride:
+        raise ValueError("user table width must equal the item row width")
+    a = MfArgsC()
+    a.users = users.data_ptr()
+    a.items = None if packed else items.data_ptr()
+    a.ratings = None if packed else ratings.data_ptr()
+    a.format = 1 if packed else 0
+    a.n_pos = users.numel(); a.num_items = 1
+    a.user_table = user_table.data_ptr(); a.user_div = int(user_div); a.user_shift = log2_or_neg(int(user_div))
+    a.lr = float(lr); a.err_mode = int(err_mode)
+    a.stats = stats.data_ptr() if stats is not None else None
+    a.nan_flag = nan_flag.data_ptr() if nan_flag is not None else None
+    a.item_tab = item_tab
+    _check(lib().fps_mf_sgd_fused_f64(C.byref(a), 4 if packed else _id_bytes(users),
+                                      sm_count(users.device.index), _stream()), "mf_sgd_fused_f64")
+    _bump()
+
+
 class NegArgsC(C.Structure):
     """Mirror of ``struct NegArgs`` (csrc/fps_sampler.cu)."""
 

@@ -521,3 +521,32 @@ def native_pack(u, i, r):
     from fps_b200.ops import native
 
     return native.pack_ratings(u, i, r)
+
+
+def test_fp64_fused_mf_step_matches_float64_reference(dev):
+    """The fp64 tier (reference precision, Vector.scala:8): one conflict-free micro-batch against torch float64."""
+    from fps_b200.models.mf.device_f64 import DeviceOnlineMFf64
+    from fps_b200.ops import native
+
+    nu, ni, k, b, lr = 3000, 2000, 10, 1500, 0.05
+    m = DeviceOnlineMFf64(nu, ni, k, range_min=-0.5, range_max=0.5, learning_rate=lr, seed=7)
+    U0, V0 = m.users[:, :k].clone(), m.items_f64[:, :k].clone()
+    assert U0.dtype == torch.float64 and float(U0.abs().max()) <= 0.5 and float(U0.std()) > 0.2
+    g = torch.Generator().manual_seed(2)
+    users = torch.randperm(nu, generator=g)[:b].int().to(dev)
+    items = torch.randperm(ni, generator=g)[:b].int().to(dev)
+    ratings = torch.rand(b, generator=g).to(dev)
+    m.step(users, items, ratings)
+    torch.cuda.synchronize()
+    u, v = U0[users.long()], V0[items.long()]
+    e = torch.sigmoid(ratings.double() - (u * v).sum(1))
+    U = U0.clone(); U[users.long()] += lr * e[:, None] * v
+    V = V0.clone(); V[items.long()] += lr * e[:, None] * u
+    torch.testing.assert_close(m.users[:, :k], U, rtol=1e-12, atol=1e-13)
+    torch.testing.assert_close(m.items_f64[:, :k], V, rtol=1e-12, atol=1e-13)
+    torch.testing.assert_close(m.predict(users, items), (U[users.long()] * V[items.long()]).sum(1),
+                               rtol=1e-12, atol=1e-13)
+    m.step(native.pack_ratings(users, items, ratings.half().float()))      # packed64 records: same kernel
+    torch.cuda.synchronize()
+    m.check_finite(); assert m.stats[1].item() == 2 * b
+    m.close()
