@@ -52,7 +52,8 @@ def main():
         server.start()
         g = torch.Generator().manual_seed(100 + rank)
         best = None
-        for it in range(a.iters + 1):
+        try:
+          for it in range(a.iters + 1):
             ids = torch.randint(0, a.keys, (a.txn,), generator=g).to(dev)
             d = torch.ones(a.txn, a.dim, device=dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -67,6 +68,9 @@ def main():
             ms = e0.elapsed_time(e1)
             if it > 0:
                 best = ms if best is None else min(best, ms)
+        except BaseException:
+            server.stop_flag_only()          # never leave a persistent kernel behind a failing run
+            raise
         if world > 1:
             with torch.cuda.stream(client.stream):      # every worker is done before any server stops
                 dist.barrier()

@@ -108,6 +108,51 @@ __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long
   return true;
 }
 
+// Multi-producer enqueue for the RESPONSE rings.  A worker's response ring for shard S is written by the
+// server warp that serves that worker's requests AND, under the lock logics, by the warps of other workers
+// that hand a released key over to a queued waiter -- several producers, all on this GPU.  Slots are
+// reserved with a local atomic, filled, and published strictly in reservation order.
+__device__ bool ring_put_mp(const RingSet& r, int ring, unsigned long long* reserve,
+                            unsigned long long* published, int op, int self, long long id, unsigned tag,
+                            const float* payload, int lane, int* err) {
+  RingHdr* h = ring_hdr(r, ring);
+  unsigned long long slot = 0;
+  int ok = 1;
+  if (lane == 0) {
+    slot = atomicAdd(reserve + ring, 1ull);
+    unsigned spins = 0;
+    while (slot - ld_acquire_sys(&h->tail) >= (unsigned long long)r.capacity) {
+      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+      __nanosleep(64);
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  if (!ok) { if (lane == 0) atomicExch(err, ERR_SPIN); return false; }
+  Entry* e = ring_entry(r, ring, slot);
+  if (lane == 0) { e->op = op; e->peer = self; e->id = id; e->tag = tag; e->pad = 0; }
+  float* dst = entry_payload(e);
+  for (int q = lane; q < r.stride; q += 32) dst[q] = payload ? payload[q] : 0.f;
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();
+    volatile unsigned long long* pub = published + ring;
+    unsigned spins = 0;
+    while (*pub != slot) {                                   // wait for the earlier reservations
+      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+      __nanosleep(64);
+    }
+    if (ok) {
+      st_release_sys(&h->head, slot + 1);
+      __threadfence();
+      *pub = slot + 1;
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok && lane == 0) atomicExch(err, ERR_SPIN);
+  return ok != 0;
+}
+
 // ============================================================================================
 // persistent server kernel
 // ============================================================================================
@@ -130,6 +175,8 @@ struct ServerArgs {
   volatile int* stop;     // host sets to 1 to drain and exit
   int* err;
   unsigned long long* counters;  // [0] pulls served, [1] pushes applied, [2] answers sent
+  unsigned long long* resp_reserve;    // [workers * lanes] slot reservation of every response ring (local)
+  unsigned long long* resp_published;  // [workers * lanes] slots published so far (in-order publish)
 };
 
 __device__ __forceinline__ float* local_row(const ServerArgs& a, long long id, long long& slot) {
@@ -162,7 +209,8 @@ __device__ void apply_update(const ServerArgs& a, float* row, const float* delta
 
 __device__ bool answer(const ServerArgs& a, int worker, int ring_lane, long long id, unsigned tag,
                        const float* row, int lane) {
-  const bool ok = ring_put(a.resp, worker * a.resp.lanes + ring_lane, OP_PULL, a.self, id, tag, row, lane, a.err);
+  const bool ok = ring_put_mp(a.resp, worker * a.resp.lanes + ring_lane, a.resp_reserve, a.resp_published,
+                              OP_PULL, a.self, id, tag, row, lane, a.err);
   if (ok && lane == 0) atomicAdd(a.counters + 2, 1ull);
   return ok;
 }

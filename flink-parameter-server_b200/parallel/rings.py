@@ -52,7 +52,7 @@ class ServerArgsC(C.Structure):
                 ("lock_mutex", C.c_void_p), ("wait_head", C.c_void_p), ("pool", C.c_void_p),
                 ("pool_next", C.c_void_p), ("free_head", C.c_void_p), ("pool_size", C.c_int),
                 ("touched", C.c_void_p), ("stop", C.c_void_p), ("err", C.c_void_p),
-                ("counters", C.c_void_p)]
+                ("counters", C.c_void_p), ("resp_reserve", C.c_void_p), ("resp_published", C.c_void_p)]
 
 
 class ClientArgsC(C.Structure):
@@ -130,6 +130,9 @@ class DeviceMessageServer:
         self.touched = z((rows + 31) // 32) if track else None
         self.stop_flag, self.err = z(1), z(1)
         self.counters = z(3, torch.int64)
+        # multi-producer response rings: reservation / in-order publish counters (fresh rings start at 0)
+        self.resp_reserve = z(rings.world * rings.lanes, torch.int64)
+        self.resp_published = z(rings.world * rings.lanes, torch.int64)
         a = ServerArgsC()
         a.req, a.resp = rings.server_sets()
         a.tab = table.table_c
@@ -139,6 +142,7 @@ class DeviceMessageServer:
         a.pool_next, a.free_head, a.pool_size = self.pool_next.data_ptr(), self.free_head.data_ptr(), pool_size
         a.touched = self.touched.data_ptr() if self.touched is not None else None
         a.stop, a.err, a.counters = self.stop_flag.data_ptr(), self.err.data_ptr(), self.counters.data_ptr()
+        a.resp_reserve, a.resp_published = self.resp_reserve.data_ptr(), self.resp_published.data_ptr()
         self.args = a
         self.stream = torch.cuda.Stream(device=dev)
         self.ctl = torch.cuda.Stream(device=dev)
@@ -178,6 +182,13 @@ class DeviceMessageServer:
         code = int(self._read(self.err)[0])
         if code:
             raise RuntimeError(f"device server: {ERRORS.get(code, code)}")
+
+    def stop_flag_only(self) -> None:
+        """Ask the kernel to exit without waiting or raising (error paths)."""
+        with torch.cuda.stream(self.ctl):
+            self.stop_flag.fill_(1)
+        self.ctl.synchronize()
+        self.running = False
 
     def _read(self, t: torch.Tensor) -> torch.Tensor:
         with torch.cuda.stream(self.ctl):

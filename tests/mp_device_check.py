@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
-    from tests.mp_util import init_dist, all_reduce_sum
+    from tests.mp_util import init_dist, all_reduce_sum, all_gather_cat
     rank, world, dev, shared = init_dist()
     from fps_b200.store.sharded_table import ShardedTable
     from fps_b200.models.mf.device import DeviceOnlineMF
@@ -136,6 +136,34 @@ def main():
         expect[torch.arange(r_, 200, 3)] += 1
     after = tab.pull(torch.arange(1000, device=dev)).cpu()
     torch.testing.assert_close(after, expect)
+    rings.close(); tab.close()
+    dist.barrier()
+    # ---- throughput path across GPUs: every rank runs pull->push(+1) transactions on the same 24 hot keys
+    #      under LockPSLogicA; hand-overs make several server warps answer into one response ring --------------
+    tab = ShardedTable(1000, 8, seed=22, init_range=(0.0, 1.0))
+    ref_hot = tab.pull(torch.arange(24, device=dev)).cpu()
+    rings = RingFabric(tab.stride, capacity=64, lanes=4)
+    server = DeviceMessageServer(tab, rings, update="add", lock="A", pool_size=1 << 16)
+    client = DeviceRingClient(tab, rings, pull_limit=128)
+    dist.barrier()
+    server.start()
+    per_key = 150
+    hot = torch.arange(24).repeat_interleave(per_key)
+    hot = hot[torch.randperm(hot.numel(), generator=torch.Generator().manual_seed(50 + rank))]
+    vals = client.transact(hot, torch.ones(hot.numel(), 8))
+    st = client.wait()
+    assert st["pulls"] == hot.numel() and st["answers"] == hot.numel() and st["credits"] == 128
+    with torch.cuda.stream(client.stream):
+        dist.barrier()
+    client.stream.synchronize()
+    server.stop()
+    dist.barrier()
+    seen = all_gather_cat(torch.stack([hot.to(dev).float(), vals[:, 0]], 1))     # (key, value seen) of every rank
+    after = tab.pull(torch.arange(24, device=dev)).cpu()
+    for k_ in range(24):
+        got = torch.sort(seen[seen[:, 0] == k_, 1].cpu() - ref_hot[k_, 0]).values
+        torch.testing.assert_close(got, torch.arange(world * per_key, dtype=torch.float32), rtol=0, atol=2e-3)
+    torch.testing.assert_close(after[:, 0], ref_hot[:, 0] + world * per_key, rtol=0, atol=2e-3)
     rings.close(); tab.close()
     dist.barrier()
     if rank == 0:

@@ -33,7 +33,17 @@ def main():
     n_users, n_items = 60, 400
     # a synthetic "week": users revisit a small personal set of items, so the learner has something to rank
     fav = {u: rng.choice(n_items, 6, replace=False) for u in range(n_users)}
-    ratings = [Rating(int(u), int(rng.choice(fav[u])), 1.0, t) for t, u in enumerate(rng.randint(0, n_users, 1500))]
+    # inside one micro-batch (50 ratings) every user and every item appears once: asynchronous SGD has no
+    # ordering contract between updates of the same row in a batch, so only collision-free batches make the
+    # N-rank and the single-rank execution comparable number by number
+    ratings, t = [], 0
+    for _ in range(30):
+        used = set()
+        for u in rng.permutation(n_users)[:50]:
+            cand = [i for i in fav[int(u)] if i not in used] or [i for i in range(n_items) if i not in used]
+            i = int(cand[rng.randint(len(cand))])
+            used.add(i)
+            ratings.append(Rating(int(u), i, 1.0, t)); t += 1
     kw = dict(numFactors=16, K=10, userMemory=0, learningRate=0.15, rangeMin=-0.1, rangeMax=0.1,
               batch_size=50, plain_residual=True, seed=5, backend="device", numUsers=n_users, numItems=n_items)
     solo_group = [dist.new_group([r]) for r in range(world)][rank]
