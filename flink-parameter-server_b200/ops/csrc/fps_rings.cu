@@ -79,18 +79,27 @@ __device__ __forceinline__ float* entry_payload(Entry* e) {
 }
 
 // Warp-cooperative enqueue (single producer per ring).  `peer` is the RING INDEX (peer * lanes + lane).
+// `tail_cache` (optional, owned by the producer) holds the last consumer tail this producer has seen: the
+// remote tail is re-read only when the ring looks full, so a put costs no NVLink round trip in the
+// common case.  Publication: every lane's stores are ordered before lane 0's st.release.sys by the
+// __syncwarp barrier (release is cumulative), so no separate system fence is needed.
 // Returns false on spin-limit.
 __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long id, unsigned tag,
-                         const float* payload, int lane, int* err) {
+                         const float* payload, int lane, int* err,
+                         unsigned long long* tail_cache = nullptr) {
   RingHdr* h = ring_hdr(r, peer);
   unsigned long long head = 0;
   int ok = 1;
   if (lane == 0) {
     head = h->head;  // only this producer writes head: a plain read of our own last value
-    unsigned spins = 0;
-    while (head - ld_acquire_sys(&h->tail) >= (unsigned long long)r.capacity) {
-      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
-      __nanosleep(64);
+    unsigned long long tail = tail_cache ? *tail_cache : 0ull;
+    if (head - tail >= (unsigned long long)r.capacity) {
+      unsigned spins = 0;
+      while (head - (tail = ld_acquire_sys(&h->tail)) >= (unsigned long long)r.capacity) {
+        if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+        __nanosleep(64);
+      }
+      if (tail_cache) *tail_cache = tail;
     }
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -101,10 +110,7 @@ __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long
   float* dst = entry_payload(e);
   for (int q = lane; q < r.stride; q += 32) dst[q] = payload ? payload[q] : 0.f;
   __syncwarp();
-  if (lane == 0) {
-    __threadfence_system();
-    st_release_sys(&h->head, head + 1);
-  }
+  if (lane == 0) st_release_sys(&h->head, head + 1);
   return true;
 }
 
@@ -113,17 +119,24 @@ __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long
 // that hand a released key over to a queued waiter -- several producers, all on this GPU.  Slots are
 // reserved with a local atomic, filled, and published strictly in reservation order.
 __device__ bool ring_put_mp(const RingSet& r, int ring, unsigned long long* reserve,
-                            unsigned long long* published, int op, int self, long long id, unsigned tag,
-                            const float* payload, int lane, int* err) {
+                            unsigned long long* published, unsigned long long* tail_cache, int op, int self,
+                            long long id, unsigned tag, const float* payload, int lane, int* err) {
   RingHdr* h = ring_hdr(r, ring);
   unsigned long long slot = 0;
   int ok = 1;
   if (lane == 0) {
     slot = atomicAdd(reserve + ring, 1ull);
-    unsigned spins = 0;
-    while (slot - ld_acquire_sys(&h->tail) >= (unsigned long long)r.capacity) {
-      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
-      __nanosleep(64);
+    // the consumer's tail as last seen by any producer of this ring (local memory, monotone): the remote
+    // tail is re-read only when the ring looks full
+    volatile unsigned long long* tc = tail_cache + ring;
+    unsigned long long tail = *tc;
+    if (slot - tail >= (unsigned long long)r.capacity) {
+      unsigned spins = 0;
+      while (slot - (tail = ld_acquire_sys(&h->tail)) >= (unsigned long long)r.capacity) {
+        if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+        __nanosleep(64);
+      }
+      atomicMax(tail_cache + ring, tail);
     }
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -135,15 +148,14 @@ __device__ bool ring_put_mp(const RingSet& r, int ring, unsigned long long* rese
   for (int q = lane; q < r.stride; q += 32) dst[q] = payload ? payload[q] : 0.f;
   __syncwarp();
   if (lane == 0) {
-    __threadfence_system();
     volatile unsigned long long* pub = published + ring;
     unsigned spins = 0;
     while (*pub != slot) {                                   // wait for the earlier reservations
       if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
-      __nanosleep(64);
+      if (spins > 8) __nanosleep(64);
     }
     if (ok) {
-      st_release_sys(&h->head, slot + 1);
+      st_release_sys(&h->head, slot + 1);                    // release: cumulative over the warp's stores
       __threadfence();
       *pub = slot + 1;
     }
@@ -177,6 +189,7 @@ struct ServerArgs {
   unsigned long long* counters;  // [0] pulls served, [1] pushes applied, [2] answers sent
   unsigned long long* resp_reserve;    // [workers * lanes] slot reservation of every response ring (local)
   unsigned long long* resp_published;  // [workers * lanes] slots published so far (in-order publish)
+  unsigned long long* resp_tail_cache; // [workers * lanes] last consumer tail seen (saves NVLink round trips)
 };
 
 __device__ __forceinline__ float* local_row(const ServerArgs& a, long long id, long long& slot) {
@@ -204,15 +217,12 @@ __device__ void apply_update(const ServerArgs& a, float* row, const float* delta
     }
   }
   __syncwarp();
-  __threadfence();
 }
 
 __device__ bool answer(const ServerArgs& a, int worker, int ring_lane, long long id, unsigned tag,
                        const float* row, int lane) {
-  const bool ok = ring_put_mp(a.resp, worker * a.resp.lanes + ring_lane, a.resp_reserve, a.resp_published,
-                              OP_PULL, a.self, id, tag, row, lane, a.err);
-  if (ok && lane == 0) atomicAdd(a.counters + 2, 1ull);
-  return ok;
+  return ring_put_mp(a.resp, worker * a.resp.lanes + ring_lane, a.resp_reserve, a.resp_published,
+                     a.resp_tail_cache, OP_PULL, a.self, id, tag, row, lane, a.err);
 }
 
 // One warp per request ring; the rings of one shard are spread over as many CTAs as needed (8 warps each),
@@ -225,11 +235,21 @@ __global__ void __launch_bounds__(32 * SERVER_WARPS)
   if (w >= a.req.n_peers * a.req.lanes) return;
   const int ring_lane = w % a.req.lanes;
   RingHdr* h = ring_hdr(a.req, w);
-  unsigned long long tail = h->tail;
+  unsigned long long tail = h->tail, tail_pub = tail;
+  unsigned long long c_pull = 0, c_push = 0, c_ans = 0;   // flushed to the global counters when idle / at exit
   unsigned idle = 0;
   while (true) {
-    const unsigned long long head = ld_acquire_sys(&h->head);
+    unsigned long long head = 0;
+    if (lane == 0) head = ld_acquire_sys(&h->head);
+    head = __shfl_sync(0xffffffffu, head, 0);
     if (tail == head) {
+      if (lane == 0) {
+        if (tail_pub != tail) { st_release_sys(&h->tail, tail); tail_pub = tail; }
+        if (c_pull | c_push | c_ans) {
+          atomicAdd(a.counters + 0, c_pull); atomicAdd(a.counters + 1, c_push); atomicAdd(a.counters + 2, c_ans);
+          c_pull = c_push = c_ans = 0;
+        }
+      }
       if (*a.stop) break;
       if (++idle > 64) __nanosleep(256);
       continue;
@@ -246,13 +266,11 @@ __global__ void __launch_bounds__(32 * SERVER_WARPS)
       if (op == OP_PULL) {
         if (lane == 0 && a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
         if (!answer(a, worker, ring_lane, id, tag, row, lane)) return;
-        if (lane == 0) atomicAdd(a.counters + 0, 1ull);
+        ++c_pull; ++c_ans;
       } else {
         apply_update(a, row, entry_payload(e), lane);
-        if (lane == 0) {
-          if (a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
-          atomicAdd(a.counters + 1, 1ull);
-        }
+        if (lane == 0 && a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
+        ++c_push;
       }
     } else {
       // ---- LockPSLogicA / B: all state changes of one row are serialised by a spin mutex ----
@@ -296,8 +314,11 @@ __global__ void __launch_bounds__(32 * SERVER_WARPS)
       granted = __shfl_sync(0xffffffffu, granted, 0);
       if (op == OP_PULL) {
         if (lane == 0) { __threadfence(); atomicExch(a.lock_mutex + slot, 0); }
-        if (granted && !answer(a, worker, ring_lane, id, tag, row, lane)) return;
-        if (lane == 0) atomicAdd(a.counters + 0, 1ull);
+        if (granted) {
+          if (!answer(a, worker, ring_lane, id, tag, row, lane)) return;
+          ++c_ans;
+        }
+        ++c_pull;
       } else {
         apply_update(a, row, entry_payload(e), lane);
         if (lane == 0) {
@@ -311,16 +332,27 @@ __global__ void __launch_bounds__(32 * SERVER_WARPS)
           }
           __threadfence();
           atomicExch(a.lock_mutex + slot, 0);
-          atomicAdd(a.counters + 1, 1ull);
         }
+        ++c_push;
         hand_worker = __shfl_sync(0xffffffffu, hand_worker, 0);
         hand_tag = __shfl_sync(0xffffffffu, hand_tag, 0);
-        if (hand_worker >= 0 && !answer(a, hand_worker, ring_lane, id, hand_tag, row, lane)) return;
+        if (hand_worker >= 0) {
+          if (!answer(a, hand_worker, ring_lane, id, hand_tag, row, lane)) return;
+          ++c_ans;
+        }
       }
     }
     ++tail;
-    if (lane == 0) st_release_sys(&h->tail, tail);
+    // hand the consumed slots back in batches (the producer re-reads our tail only when its ring looks full)
+    if (lane == 0 && tail - tail_pub >= (unsigned long long)(a.req.capacity / 4)) {
+      st_release_sys(&h->tail, tail);
+      tail_pub = tail;
+    }
     __syncwarp();
+  }
+  if (lane == 0) {
+    st_release_sys(&h->tail, tail);
+    atomicAdd(a.counters + 0, c_pull); atomicAdd(a.counters + 1, c_push); atomicAdd(a.counters + 2, c_ans);
   }
 }
 
@@ -478,7 +510,8 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
   const int end = a.seg[r + 1];
   if (pos == end) return;
   RingHdr* hr = ring_hdr(a.resp, r);
-  unsigned long long rtail = hr->tail;
+  unsigned long long rtail = hr->tail, rtail_pub = rtail;
+  unsigned long long req_tail_cache = 0;     // the server's tail of my request ring, as last seen
   int outstanding = 0;
   const int max_out = a.resp.capacity;
   const int stride = a.req.stride;
@@ -499,20 +532,26 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
         for (int q = lane; q < stride; q += 32) a.out_vals[(size_t)msg * stride + q] = src[q];
         __syncwarp();
         ++rtail;
-        if (lane == 0) st_release_sys(&hr->tail, rtail);
         --outstanding; ++n_ans;
         if (a.mode == TXN_PULL_PUSH) {
-          if (!ring_put(a.req, r, OP_PUSH, a.self, id, msg, a.deltas + (size_t)msg * stride, lane, a.err)) return;
+          if (!ring_put(a.req, r, OP_PUSH, a.self, id, msg, a.deltas + (size_t)msg * stride, lane, a.err,
+                        &req_tail_cache))
+            return;
           ++n_push;
         }
         if (lane == 0) atomicAdd(a.credits, 1);            // onPullRecv done: release the credit
         progressed = true;
       }
+      if (lane == 0 && rtail != rtail_pub) {               // one release per drained batch of answers
+        st_release_sys(&hr->tail, rtail);
+        rtail_pub = rtail;
+      }
     }
     // ---- issue the next message -------------------------------------------------------------------------------
     if (pos < end) {
       if (a.mode == TXN_PUSH_ONLY) {
-        if (!ring_put(a.req, r, OP_PUSH, a.self, a.ids[pos], (unsigned)pos, a.deltas + (size_t)pos * stride, lane, a.err))
+        if (!ring_put(a.req, r, OP_PUSH, a.self, a.ids[pos], (unsigned)pos, a.deltas + (size_t)pos * stride, lane, a.err,
+                      &req_tail_cache))
           return;
         ++pos; ++n_push;
         progressed = true;
@@ -524,7 +563,8 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
         }
         got = __shfl_sync(0xffffffffu, got, 0);
         if (got) {
-          if (!ring_put(a.req, r, OP_PULL, a.self, a.ids[pos], (unsigned)pos, nullptr, lane, a.err)) return;
+          if (!ring_put(a.req, r, OP_PULL, a.self, a.ids[pos], (unsigned)pos, nullptr, lane, a.err, &req_tail_cache))
+            return;
           ++pos; ++outstanding; ++n_pull;
           progressed = true;
         }

@@ -52,7 +52,8 @@ class ServerArgsC(C.Structure):
                 ("lock_mutex", C.c_void_p), ("wait_head", C.c_void_p), ("pool", C.c_void_p),
                 ("pool_next", C.c_void_p), ("free_head", C.c_void_p), ("pool_size", C.c_int),
                 ("touched", C.c_void_p), ("stop", C.c_void_p), ("err", C.c_void_p),
-                ("counters", C.c_void_p), ("resp_reserve", C.c_void_p), ("resp_published", C.c_void_p)]
+                ("counters", C.c_void_p), ("resp_reserve", C.c_void_p), ("resp_published", C.c_void_p),
+                ("resp_tail_cache", C.c_void_p)]
 
 
 class ClientArgsC(C.Structure):
@@ -133,6 +134,7 @@ class DeviceMessageServer:
         # multi-producer response rings: reservation / in-order publish counters (fresh rings start at 0)
         self.resp_reserve = z(rings.world * rings.lanes, torch.int64)
         self.resp_published = z(rings.world * rings.lanes, torch.int64)
+        self.resp_tail_cache = z(rings.world * rings.lanes, torch.int64)
         a = ServerArgsC()
         a.req, a.resp = rings.server_sets()
         a.tab = table.table_c
@@ -143,6 +145,7 @@ class DeviceMessageServer:
         a.touched = self.touched.data_ptr() if self.touched is not None else None
         a.stop, a.err, a.counters = self.stop_flag.data_ptr(), self.err.data_ptr(), self.counters.data_ptr()
         a.resp_reserve, a.resp_published = self.resp_reserve.data_ptr(), self.resp_published.data_ptr()
+        a.resp_tail_cache = self.resp_tail_cache.data_ptr()
         self.args = a
         self.stream = torch.cuda.Stream(device=dev)
         self.ctl = torch.cuda.Stream(device=dev)

@@ -540,6 +540,7 @@ def test_fp64_fused_mf_step_matches_float64_reference(dev):
     torch.cuda.synchronize()
     u, v = U0[users.long()], V0[items.long()]
     e = torch.sigmoid(ratings.double() - (u * v).sum(1))
+    lr = float(torch.tensor(lr, dtype=torch.float32))        # the learning rate travels as an fp32 kernel argument
     U = U0.clone(); U[users.long()] += lr * e[:, None] * v
     V = V0.clone(); V[items.long()] += lr * e[:, None] * u
     torch.testing.assert_close(m.users[:, :k], U, rtol=1e-12, atol=1e-13)
