@@ -50,7 +50,7 @@ class DeviceWideAndDeep:
         if self._rows is None or self._rows.shape[0] != flat.numel():
             self._rows = torch.empty((flat.numel(), self.table.stride), dtype=torch.float32, device=self.dev)
             self._drows = torch.empty_like(self._rows)
-        native.pull_gather(self.table.table_c, flat, self._rows,
+        native.pull_gather(self.table.table_c, flat, self._rows, max_inflight_rows=self.pull_limit,
                            credits=self.table._credits(self.pull_limit, self.dev) if self.pull_limit > 0 else None)
         return self._rows
 

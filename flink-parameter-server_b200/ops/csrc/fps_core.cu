@@ -295,12 +295,13 @@ template <typename IdT, int FMT>
 static int dispatch_mf(const MfArgs& a, int max_inflight, int num_sms, cudaStream_t s) {
   const int nvec = a.item_tab.stride >> 2;
   const int v = g_mf_reg_variant;
-  if (a.credits != nullptr) {   // device credit-counter pull limiter: full grid, the counter bounds the pulls in flight
-    if (nvec <= 4) return launch_mf<IdT, 4, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
-    if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
-    if (nvec <= 16) return launch_mf<IdT, 16, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
-    if (nvec <= 32) return launch_mf<IdT, 32, 1, 1, 4, FMT, 0, 0, 1>(a, 0, num_sms, s);
-    if (nvec <= 128) return launch_mf<IdT, 32, 4, 1, 2, FMT, 0, 0, 1>(a, 0, num_sms, s);
+  if (a.credits != nullptr) {   // device credit-counter pull limiter: the counter bounds the pulls in flight;
+    const int cap = 2 * max_inflight;  // the grid is trimmed to ~2x the credits (fewer contenders on the counter)
+    if (nvec <= 4) return launch_mf<IdT, 4, 1, 1, 4, FMT, 0, 0, 1>(a, cap, num_sms, s);
+    if (nvec <= 8) return launch_mf<IdT, 8, 1, 1, 4, FMT, 0, 0, 1>(a, cap, num_sms, s);
+    if (nvec <= 16) return launch_mf<IdT, 16, 1, 1, 4, FMT, 0, 0, 1>(a, cap, num_sms, s);
+    if (nvec <= 32) return launch_mf<IdT, 32, 1, 1, 4, FMT, 0, 0, 1>(a, cap, num_sms, s);
+    if (nvec <= 128) return launch_mf<IdT, 32, 4, 1, 2, FMT, 0, 0, 1>(a, cap, num_sms, s);
     return -1000;
   }
   if (a.out_every > 0) {   // with the E5 output stream (one row in flight per lane-group, 4 CTAs/SM)
@@ -581,7 +582,9 @@ extern "C" int fps_pull_gather(const ShardTable* t, const void* ids, int id_byte
     return launch_wide<0>(t, ids, id_bytes, n, out, out_stride, 1.f, num_sms, stream);
   const int lpr = pick_lpr(t->stride >> 2);
   int grid = row_grid(n, lpr, num_sms);
-  if (credits == nullptr) grid = limit_grid(grid, lpr, max_inflight_rows);
+  // static limiter: the grid IS the bound.  Credit counter: the counter is the bound; the grid is only
+  // trimmed to ~2x the credits so that thousands of lane-groups do not fight over a handful of credits
+  grid = limit_grid(grid, lpr, credits == nullptr ? max_inflight_rows : 2 * max_inflight_rows);
   if (id_bytes == 4) {
     FPS_DISPATCH_LPR(fps_pull_gather_kernel, int, lpr, grid, stream, *t, (const int*)ids, n, out,
                      out_stride, touch, credits)

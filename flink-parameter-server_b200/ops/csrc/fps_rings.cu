@@ -114,6 +114,39 @@ __device__ bool ring_put(const RingSet& r, int peer, int op, int self, long long
   return true;
 }
 
+// ---- lane-per-message helpers (small payloads: one lane moves a whole entry) ----------------------------
+#define FPS_BATCH_MAX_STRIDE 32     // floats; wider payloads use the warp-cooperative per-message paths
+__device__ __forceinline__ void entry_write(Entry* e, int op, int self, long long id, unsigned tag,
+                                            const float* payload, int stride) {
+  e->op = op; e->peer = self; e->id = id; e->tag = tag; e->pad = 0;
+  if (payload != nullptr) {
+    float* dst = entry_payload(e);
+    if ((stride & 3) == 0) {
+      for (int q = 0; q < stride; q += 4)
+        *reinterpret_cast<float4*>(dst + q) = *reinterpret_cast<const float4*>(payload + q);
+    } else {
+      for (int q = 0; q < stride; ++q) dst[q] = payload[q];
+    }
+  }
+}
+// producer side of an SPSC ring: make sure `n` more entries fit behind `head` (lane 0 spins, result broadcast)
+__device__ __forceinline__ bool ring_reserve_space(RingHdr* h, unsigned long long head, int n, int capacity,
+                                                   unsigned long long* tail_cache, int lane, int* err) {
+  int ok = 1;
+  if (lane == 0 && head + (unsigned long long)n - *tail_cache > (unsigned long long)capacity) {
+    unsigned spins = 0;
+    unsigned long long tail;
+    while (head + (unsigned long long)n - (tail = ld_acquire_sys(&h->tail)) > (unsigned long long)capacity) {
+      if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+      __nanosleep(64);
+    }
+    *tail_cache = tail;
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok && lane == 0) atomicExch(err, ERR_SPIN);
+  return ok != 0;
+}
+
 // Multi-producer enqueue for the RESPONSE rings.  A worker's response ring for shard S is written by the
 // server warp that serves that worker's requests AND, under the lock logics, by the warps of other workers
 // that hand a released key over to a queued waiter -- several producers, all on this GPU.  Slots are
@@ -255,6 +288,101 @@ __global__ void __launch_bounds__(32 * SERVER_WARPS)
       continue;
     }
     idle = 0;
+    if (a.lock_mode == LOCK_NONE && a.tab.stride <= FPS_BATCH_MAX_STRIDE) {
+      // ---- lane-per-message batch: up to 32 requests of this ring at once ---------------------------------
+      const int n = (int)min((unsigned long long)32, head - tail);
+      const bool mine = lane < n;
+      Entry* e = mine ? ring_entry(a.req, w, tail + lane) : nullptr;
+      const int op = mine ? e->op : 0;
+      const long long id = mine ? e->id : (long long)(-1 - lane);
+      const unsigned tag = mine ? e->tag : 0u;
+      const int worker = w / a.req.lanes;
+      long long slot = 0;
+      float* row = mine ? local_row(a, id, slot) : nullptr;
+      // requests for the same key keep their ring order: they are handled in successive rounds
+      const unsigned peers = __match_any_sync(0xffffffffu, id);
+      const int my_round = __popc(peers & ((1u << lane) - 1u));
+      int rounds = my_round;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+      // the answers of this batch go to ONE response ring: reserve their slots together
+      const unsigned pull_mask = __ballot_sync(0xffffffffu, mine && op == OP_PULL);
+      const int np = __popc(pull_mask);
+      const int ring = worker * a.resp.lanes + ring_lane;
+      RingHdr* rh = ring_hdr(a.resp, ring);
+      unsigned long long base = 0;
+      int ok = 1;
+      if (np > 0) {
+        if (lane == 0) {
+          base = atomicAdd(a.resp_reserve + ring, (unsigned long long)np);
+          volatile unsigned long long* tc = a.resp_tail_cache + ring;
+          unsigned long long rt = *tc;
+          if (base + np - rt > (unsigned long long)a.resp.capacity) {
+            unsigned spins = 0;
+            while (base + np - (rt = ld_acquire_sys(&rh->tail)) > (unsigned long long)a.resp.capacity) {
+              if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+              __nanosleep(64);
+            }
+            atomicMax(a.resp_tail_cache + ring, rt);
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!ok) { if (lane == 0) atomicExch(a.err, ERR_SPIN); return; }
+      }
+      const unsigned long long my_slot = base + (unsigned long long)__popc(pull_mask & ((1u << lane) - 1u));
+      for (int rd = 0; rd <= rounds; ++rd) {
+        if (mine && my_round == rd) {
+          if (a.touched) atomicOr(a.touched + (slot >> 5), 1u << (slot & 31));
+          if (op == OP_PULL) {
+            entry_write(ring_entry(a.resp, ring, my_slot), OP_PULL, a.self, id, tag, row, a.resp.stride);
+          } else {
+            const float* d = entry_payload(e);
+            for (int q = 0; q < a.tab.stride; ++q) {
+              if (a.update_op == UPD_ADD) atomicAdd(row + q, d[q]);
+              else if (a.update_op == UPD_ASSIGN) row[q] = d[q];
+              else {
+                int* p = reinterpret_cast<int*>(row + q);
+                int old = *p, assumed;
+                do {
+                  assumed = old;
+                  const float cur = __int_as_float(assumed);
+                  const float nv = (a.update_op == UPD_MAX) ? fmaxf(cur, d[q]) : fminf(cur, d[q]);
+                  old = atomicCAS(p, assumed, __float_as_int(nv));
+                } while (old != assumed);
+              }
+            }
+          }
+        }
+        __threadfence();     // a later round (same key) must see this round's row
+        __syncwarp();
+      }
+      if (np > 0) {          // publish the batch of answers, in reservation order
+        if (lane == 0) {
+          volatile unsigned long long* pub = a.resp_published + ring;
+          unsigned spins = 0;
+          while (*pub != base) {
+            if (++spins > FPS_SPIN_LIMIT) { ok = 0; break; }
+            if (spins > 8) __nanosleep(64);
+          }
+          if (ok) {
+            st_release_sys(&rh->head, base + np);
+            __threadfence();
+            *pub = base + np;
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) { if (lane == 0) atomicExch(a.err, ERR_SPIN); return; }
+      }
+      c_pull += np; c_ans += np; c_push += n - np;
+      tail += n;
+      if (lane == 0 && tail - tail_pub >= (unsigned long long)(a.req.capacity / 4)) {
+        st_release_sys(&h->tail, tail);
+        tail_pub = tail;
+      }
+      __syncwarp();
+      continue;
+    }
     Entry* e = ring_entry(a.req, w, tail);
     const int op = e->op;
     const long long id = e->id;
@@ -509,37 +637,65 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
   int pos = a.seg[r];
   const int end = a.seg[r + 1];
   if (pos == end) return;
+  RingHdr* hq = ring_hdr(a.req, r);
   RingHdr* hr = ring_hdr(a.resp, r);
+  unsigned long long qhead = hq->head;            // I am the only producer of this request ring
+  unsigned long long qtail_cache = 0;             // the server's tail of it, as last seen
   unsigned long long rtail = hr->tail, rtail_pub = rtail;
-  unsigned long long req_tail_cache = 0;     // the server's tail of my request ring, as last seen
   int outstanding = 0;
   const int max_out = a.resp.capacity;
   const int stride = a.req.stride;
+  const bool lane_batches = stride <= FPS_BATCH_MAX_STRIDE;   // one lane moves one message
   unsigned long long n_pull = 0, n_push = 0, n_ans = 0;
   unsigned idle = 0;
   while (pos < end || outstanding > 0) {
     bool progressed = false;
-    // ---- consume answers ------------------------------------------------------------------------------------
+    // ---- consume answers (and, in PULL_PUSH mode, send the pushes they trigger) -------------------------------
     if (outstanding > 0) {
       unsigned long long rhead = 0;
       if (lane == 0) rhead = ld_acquire_sys(&hr->head);
-      rhead = __shfl_sync(0xffffffffu, rhead, 0);           // one observation for the whole warp
+      rhead = __shfl_sync(0xffffffffu, rhead, 0);            // one observation for the whole warp
       while (rtail != rhead) {
-        Entry* e = ring_entry(a.resp, r, rtail);
-        const unsigned msg = e->tag;
-        const long long id = e->id;
-        const float* src = entry_payload(e);
-        for (int q = lane; q < stride; q += 32) a.out_vals[(size_t)msg * stride + q] = src[q];
-        __syncwarp();
-        ++rtail;
-        --outstanding; ++n_ans;
-        if (a.mode == TXN_PULL_PUSH) {
-          if (!ring_put(a.req, r, OP_PUSH, a.self, id, msg, a.deltas + (size_t)msg * stride, lane, a.err,
-                        &req_tail_cache))
-            return;
-          ++n_push;
+        if (lane_batches) {
+          const int n = (int)min((unsigned long long)32, rhead - rtail);
+          const bool mine = lane < n;
+          unsigned msg = 0;
+          long long id = 0;
+          if (mine) {
+            Entry* e = ring_entry(a.resp, r, rtail + lane);
+            msg = e->tag; id = e->id;
+            const float* src = entry_payload(e);
+            float* dst = a.out_vals + (size_t)msg * stride;
+            for (int q = 0; q < stride; ++q) dst[q] = src[q];
+          }
+          if (a.mode == TXN_PULL_PUSH) {
+            if (!ring_reserve_space(hq, qhead, n, a.req.capacity, &qtail_cache, lane, a.err)) return;
+            if (mine)
+              entry_write(ring_entry(a.req, r, qhead + lane), OP_PUSH, a.self, id, msg,
+                          a.deltas + (size_t)msg * stride, stride);
+            __syncwarp();
+            qhead += n;
+            if (lane == 0) st_release_sys(&hq->head, qhead);
+            n_push += n;
+          }
+          rtail += n; outstanding -= n; n_ans += n;
+          if (lane == 0) atomicAdd(a.credits, n);           // onPullRecv done: release the credits
+        } else {
+          Entry* e = ring_entry(a.resp, r, rtail);
+          const unsigned msg = e->tag;
+          const long long id = e->id;
+          const float* src = entry_payload(e);
+          for (int q = lane; q < stride; q += 32) a.out_vals[(size_t)msg * stride + q] = src[q];
+          __syncwarp();
+          ++rtail; --outstanding; ++n_ans;
+          if (a.mode == TXN_PULL_PUSH) {
+            if (!ring_put(a.req, r, OP_PUSH, a.self, id, msg, a.deltas + (size_t)msg * stride, lane, a.err,
+                          &qtail_cache))
+              return;
+            ++n_push;
+          }
+          if (lane == 0) atomicAdd(a.credits, 1);
         }
-        if (lane == 0) atomicAdd(a.credits, 1);            // onPullRecv done: release the credit
         progressed = true;
       }
       if (lane == 0 && rtail != rtail_pub) {               // one release per drained batch of answers
@@ -547,27 +703,37 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
         rtail_pub = rtail;
       }
     }
-    // ---- issue the next message -------------------------------------------------------------------------------
+    // ---- issue the next messages ---------------------------------------------------------------------------------
     if (pos < end) {
-      if (a.mode == TXN_PUSH_ONLY) {
-        if (!ring_put(a.req, r, OP_PUSH, a.self, a.ids[pos], (unsigned)pos, a.deltas + (size_t)pos * stride, lane, a.err,
-                      &req_tail_cache))
-          return;
-        ++pos; ++n_push;
-        progressed = true;
-      } else if (outstanding < max_out) {
+      int k = min(lane_batches ? 32 : 1, end - pos);
+      if (a.mode != TXN_PUSH_ONLY) {
+        k = min(k, max_out - outstanding);
         int got = 0;
-        if (lane == 0) {                                    // one non-blocking attempt on the credit counter
+        if (lane == 0 && k > 0) {                            // one non-blocking attempt on the credit counter
           const int cur = *reinterpret_cast<volatile int*>(a.credits);
-          if (cur > 0 && atomicCAS(a.credits, cur, cur - 1) == cur) got = 1;
+          const int take = min(k, cur);
+          if (take > 0 && atomicCAS(a.credits, cur, cur - take) == cur) got = take;
         }
-        got = __shfl_sync(0xffffffffu, got, 0);
-        if (got) {
-          if (!ring_put(a.req, r, OP_PULL, a.self, a.ids[pos], (unsigned)pos, nullptr, lane, a.err, &req_tail_cache))
+        k = __shfl_sync(0xffffffffu, got, 0);
+      }
+      if (k > 0) {
+        const int op = a.mode == TXN_PUSH_ONLY ? OP_PUSH : OP_PULL;
+        if (lane_batches) {
+          if (!ring_reserve_space(hq, qhead, k, a.req.capacity, &qtail_cache, lane, a.err)) return;
+          if (lane < k)
+            entry_write(ring_entry(a.req, r, qhead + lane), op, a.self, a.ids[pos + lane], (unsigned)(pos + lane),
+                        op == OP_PUSH ? a.deltas + (size_t)(pos + lane) * stride : nullptr, stride);
+          __syncwarp();
+          qhead += k;
+          if (lane == 0) st_release_sys(&hq->head, qhead);
+        } else {
+          if (!ring_put(a.req, r, op, a.self, a.ids[pos], (unsigned)pos,
+                        op == OP_PUSH ? a.deltas + (size_t)pos * stride : nullptr, lane, a.err, &qtail_cache))
             return;
-          ++pos; ++outstanding; ++n_pull;
-          progressed = true;
         }
+        pos += k;
+        if (op == OP_PULL) { outstanding += k; n_pull += k; } else { n_push += k; }
+        progressed = true;
       }
     }
     if (progressed) {

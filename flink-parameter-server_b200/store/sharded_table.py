@@ -142,6 +142,7 @@ class ShardedTable:
         if out is None:
             out = torch.empty((ids.numel(), self.dim), dtype=torch.float32, device=ids.device)
         native.pull_gather(self._table_on(ids.device), ids, out, touch=self.track_touched,
+                           max_inflight_rows=pull_limit,
                            credits=self._credits(pull_limit, ids.device) if pull_limit > 0 else None)
         METRICS.inc("ps_pull_rows", ids.numel())
         return out
