@@ -57,7 +57,7 @@ class ReplicaCache:
         # seen after ~sync_every/2 steps on average.  An explicit flush_count / sync_interval_ms flushes
         # whole destination buffers when the device-side policy fires.
         self.sliced = flush_count is None and sync_interval_ms is None and self.sync_every > 1
-        self.n_ctas = int(os.environ.get("FPS_EXCHANGE_CTAS", 48 if exchange_ctas is None else exchange_ctas))
+        self.n_ctas = int(os.environ.get("FPS_EXCHANGE_CTAS", 64 if exchange_ctas is None else exchange_ctas))
         self.stages = int(os.environ.get("FPS_EXCHANGE_STAGES", 4 if stages is None else stages))
         self.sequential = os.environ.get("FPS_EXCHANGE_SEQUENTIAL", "0") == "1"
         self.max_outstanding = max(1, int(max_outstanding))
