@@ -120,10 +120,10 @@ __device__ __forceinline__ void entry_write(Entry* e, int op, int self, long lon
                                             const float* payload, int stride) {
   e->op = op; e->peer = self; e->id = id; e->tag = tag; e->pad = 0;
   if (payload != nullptr) {
-    float* dst = entry_payload(e);
-    if ((stride & 3) == 0) {
-      for (int q = 0; q < stride; q += 4)
-        *reinterpret_cast<float4*>(dst + q) = *reinterpret_cast<const float4*>(payload + q);
+    float* dst = entry_payload(e);       // 8-byte aligned (24-byte header inside a 16-byte aligned entry)
+    if ((stride & 1) == 0 && (reinterpret_cast<unsigned long long>(payload) & 7ull) == 0) {
+      for (int q = 0; q < stride; q += 2)
+        *reinterpret_cast<float2*>(dst + q) = *reinterpret_cast<const float2*>(payload + q);
     } else {
       for (int q = 0; q < stride; ++q) dst[q] = payload[q];
     }
