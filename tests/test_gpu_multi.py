@@ -12,7 +12,7 @@ import torch
 
 from tests.mp_util import REPO, launch_cmd
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]    # torchrun children: their own 420 s limit applies first
 
 
 def _run(script: str, world: int, port: int, ok: str, timeout: int = 420):

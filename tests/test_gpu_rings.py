@@ -11,7 +11,7 @@ import sys
 
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
