@@ -40,6 +40,18 @@ class PSOfflineMatrixFactorizationWorker(CtorFork, WorkerLogic):
         self.workerThread: Optional[threading.Thread] = None
         self._lock = threading.Lock()
         self._rnd = random.Random(seed)
+        self._seed_args = (numFactors, rangeMin, rangeMax, userMemory, negativeSampleRate, seed)
+
+    def open(self):
+        """Per-subtask random streams for seeded runs (see PSOnlineMatrixFactorizationWorker.open)."""
+        numFactors, rangeMin, rangeMax, userMemory, rate, seed = self._seed_args
+        idx = getattr(self, "subtaskIndex", 0)
+        if seed is not None and idx:
+            sub = (int(seed) * 1000003 + 7919 * idx) & 0x7FFFFFFF
+            self.factorInitDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax, sub)
+            self._init = None
+            self.sampler = NegativeSampler(userMemory, rate, sub + 1)
+            self._rnd = random.Random(sub + 2)
 
     def onRecv(self, value, ps):
         if isinstance(value, EOF):
@@ -109,6 +121,11 @@ def psOfflineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: fl
     holder = {}
 
     def paramInit(i):
+        if seed is not None:
+            # a pure function of (seed, id): deterministic whatever the interleaving of the PS shard
+            # threads, which all share this closure (the device and native tiers do the same with Philox)
+            rnd = random.Random((int(seed) + 1) * 1000003 + int(i))
+            return np.array([rangeMin + (rangeMax - rangeMin) * rnd.random() for _ in range(numFactors)])
         if "f" not in holder:
             holder["f"] = initDesc.open()
         return holder["f"].nextFactor(i)

@@ -69,12 +69,25 @@ class PSOnlineMatrixFactorizationWorker(WorkerLogic):
     def __init__(self, numFactors: int, rangeMin: float, rangeMax: float, learningRate: float,
                  userMemory: int, negativeSampleRate: int, seed: Optional[int] = None,
                  plain_residual: bool = False):
+        self._args = (numFactors, rangeMin, rangeMax, userMemory, negativeSampleRate, seed)
         self.factorInitDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax, seed)
         self._init = None
         self.factorUpdate = SGDUpdater(learningRate, plain_residual)
         self.userVectors: Dict[int, np.ndarray] = {}
         self.ratingBuffer: Dict[int, deque] = {}
         self.sampler = NegativeSampler(userMemory, negativeSampleRate, seed)
+
+    def open(self):
+        """Seeded runs: every worker subtask gets its OWN random stream (init + negative sampling); the
+        engine tells the copy which subtask it is (``subtaskIndex``).  Identical streams would give the n-th
+        new user of every worker the same vector and the same negatives."""
+        numFactors, rangeMin, rangeMax, userMemory, rate, seed = self._args
+        idx = getattr(self, "subtaskIndex", 0)
+        if seed is not None and idx:
+            sub = (int(seed) * 1000003 + 7919 * idx) & 0x7FFFFFFF
+            self.factorInitDesc = RangedRandomFactorInitializerDescriptor(numFactors, rangeMin, rangeMax, sub)
+            self._init = None
+            self.sampler = NegativeSampler(userMemory, rate, sub + 1)
 
     def _factor_init(self):
         if self._init is None:
@@ -130,6 +143,11 @@ def psOnlineMF(src, numFactors: int = 10, rangeMin: float = -0.01, rangeMax: flo
     holder = {}
 
     def paramInit(i):
+        if seed is not None:
+            # a pure function of (seed, id): deterministic whatever the interleaving of the PS shard
+            # threads, which all share this closure (the device and native tiers do the same with Philox)
+            rnd = random.Random((int(seed) + 1) * 1000003 + int(i))
+            return np.array([rangeMin + (rangeMax - rangeMin) * rnd.random() for _ in range(numFactors)])
         if "f" not in holder:
             holder["f"] = initDesc.open()
         return holder["f"].nextFactor(i)

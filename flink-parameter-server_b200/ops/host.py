@@ -116,6 +116,17 @@ def mf_train(users: torch.Tensor, items: torch.Tensor, ratings: torch.Tensor, nu
 PA_ALGOS = {"PA": 0, "PAI": 1, "PAII": 2}
 
 
+def _check_csr(rp: np.ndarray, c: np.ndarray, v: np.ndarray, n: int) -> None:
+    """The pointers go straight to C: a malformed CSR would read out of bounds there."""
+    if rp.ndim != 1 or rp.shape[0] != n + 1:
+        raise ValueError(f"row_ptr must have n + 1 = {n + 1} entries, got {rp.shape}")
+    if n and (rp[0] != 0 or np.any(np.diff(rp) < 0)):
+        raise ValueError("row_ptr must start at 0 and be non-decreasing")
+    nnz = int(rp[-1]) if rp.shape[0] else 0
+    if c.shape[0] != nnz or v.shape[0] != nnz:
+        raise ValueError(f"cols / vals must have row_ptr[-1] = {nnz} entries, got {c.shape[0]} / {v.shape[0]}")
+
+
 def pa_binary(row_ptr, cols, vals, labels, feature_count: int, algo: str = "PA", aggressiveness: float = 0.0,
               workers: int = 4, servers: int = 4, pull_limit: int = 10000, range_partitioning: bool = False,
               weights=None):
@@ -127,6 +138,7 @@ def pa_binary(row_ptr, cols, vals, labels, feature_count: int, algo: str = "PA",
     v = np.ascontiguousarray(np.asarray(vals, dtype=np.float32))
     y = np.ascontiguousarray(np.asarray(labels, dtype=np.int32))
     n = int(y.shape[0])
+    _check_csr(rp, c, v, n)
     if weights is None:
         weights = np.zeros(int(feature_count), dtype=np.float32)
     if weights.dtype != np.float32 or not weights.flags["C_CONTIGUOUS"] or weights.shape[0] != feature_count:
@@ -161,6 +173,7 @@ def pa_multiclass(row_ptr, cols, vals, labels, feature_count: int, num_labels: i
     v = np.ascontiguousarray(np.asarray(vals, dtype=np.float32))
     y = np.ascontiguousarray(np.asarray(labels, dtype=np.int32))
     n, L = int(y.shape[0]), int(num_labels)
+    _check_csr(rp, c, v, n)
     if weights is None:
         weights = np.zeros((int(feature_count), L), dtype=np.float32)
     if weights.dtype != np.float32 or not weights.flags["C_CONTIGUOUS"] or weights.shape != (feature_count, L):

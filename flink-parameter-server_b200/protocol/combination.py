@@ -37,6 +37,12 @@ class Combinable:
     def reset(self) -> None:
         self._send = False
 
+    def clear(self) -> None:
+        """The buffer was swapped out: forget everything counted / flagged for the old buffer, so the next
+        batch is measured from zero (a stale count would make the next flush fire early, a stale
+        ``containsData`` would make the timer fire on an empty buffer)."""
+        self._send = False
+
     def fork(self) -> "Combinable":
         raise NotImplementedError
 
@@ -60,6 +66,10 @@ class CountLogic(Combinable):
         if self.sendCondition():
             self.send(callback, collectAnswerMsg)
             self.count = 0
+
+    def clear(self) -> None:
+        super().clear()
+        self.count = 0
 
     def fork(self) -> "CountLogic":
         return CountLogic(self.max)
@@ -99,6 +109,10 @@ class TimerLogic(Combinable):
                                             daemon=True)
             self._thread.start()
 
+    def clear(self) -> None:
+        super().clear()
+        self.containsData = False
+
     def fork(self) -> "TimerLogic":
         return TimerLogic(self.interval)
 
@@ -123,7 +137,7 @@ class CombinationLogic:
             if self.condition(self.combinables) and self.data:
                 batch, self.data = self.data, []
                 for c in self.combinables:
-                    c.reset()
+                    c.clear()
                 collect(batch)
 
     def logic(self, func: Callable[[List[Any]], None], collect: Callable[[List[Any]], None]) -> None:
@@ -132,14 +146,17 @@ class CombinationLogic:
             for c in self.combinables:
                 c.logic(func, self.checkAndSend, collect)
 
-    def flush(self, collect: Callable[[List[Any]], None]) -> None:
-        """Unconditional flush (used at termination so no message is stranded)."""
+    def flush(self, collect: Callable[[List[Any]], None]) -> bool:
+        """Unconditional flush (used at termination so no message is stranded).  Returns whether
+        anything was emitted."""
         with self._lock:
             if self.data:
                 batch, self.data = self.data, []
                 for c in self.combinables:
-                    c.reset()
+                    c.clear()
                 collect(batch)
+                return True
+        return False
 
     def fork(self) -> "CombinationLogic":
         return CombinationLogic(self.condition, [c.fork() for c in self.combinables])

@@ -143,10 +143,11 @@ class _PerDestinationBatcher:
     def _add(self, single_msg, collect) -> None:
         self._logic_for(single_msg).logic(lambda buf: buf.append(single_msg), collect)
 
-    def flush(self, collectAnswerMsg) -> None:
-        self._proto.flush(collectAnswerMsg)
+    def flush(self, collectAnswerMsg) -> bool:
+        emitted = bool(self._proto.flush(collectAnswerMsg))
         for lg in list(self._logics.values()):
-            lg.flush(collectAnswerMsg)
+            emitted = bool(lg.flush(collectAnswerMsg)) or emitted
+        return emitted
 
     def close(self) -> None:
         self._proto.close()

@@ -33,6 +33,21 @@ from .stream import DataStream, ResultStream, as_stream
 _DATA, _ANSWER, _REQ, _STOP = 0, 1, 2, 3
 
 
+def assign_subtask(obj: Any, index: int, parallelism: int, depth: int = 0) -> None:
+    """Tell a per-subtask logic copy (and the logics it wraps) which subtask it is -- Flink's
+    ``getIndexOfThisSubtask``; seeded logics derive their own random stream from it."""
+    if obj is None or depth > 4:
+        return
+    try:
+        obj.subtaskIndex, obj.subtaskParallelism = int(index), int(parallelism)
+    except Exception:   # objects with __slots__ / read-only attributes
+        return
+    for name in ("inner", "logic", "workerLogic"):
+        sub = obj.__dict__.get(name) if hasattr(obj, "__dict__") else None
+        if sub is not None and (hasattr(sub, "onRecv") or hasattr(sub, "onPullRecv")):
+            assign_subtask(sub, index, parallelism, depth + 1)
+
+
 def clone_logic(obj: Any) -> Any:
     """Per-subtask copy of a logic / sender object (Flink serialises one copy per subtask)."""
     if hasattr(obj, "fork") and callable(obj.fork):
@@ -172,6 +187,10 @@ class LocalEngine:
         w_send = [clone_logic(workerSender) for _ in range(self.wP)]
         w_recv = [clone_logic(workerReceiver) for _ in range(self.wP)]
         p_logic = [clone_logic(psLogic) for _ in range(self.psP)]
+        for i, lg in enumerate(w_logic):
+            assign_subtask(lg, i, self.wP)
+        for j, lg in enumerate(p_logic):
+            assign_subtask(lg, j, self.psP)
         p_send = [clone_logic(psSender) for _ in range(self.psP)]
         p_recv = [clone_logic(psReceiver) for _ in range(self.psP)]
         for s in w_send:
@@ -304,12 +323,15 @@ class LocalEngine:
             idle = act.idle_for()
             if idle > 0.0 or (act.inflight == 0 and act.sources_open == 0):
                 if not flushed_idle:
-                    # flush batching senders; they may produce new traffic
+                    # flush batching senders; they may produce new traffic.  Only a FULL pass over every
+                    # sender that emitted nothing proves that no message is stranded: a PS thread may
+                    # buffer answers to just-flushed pulls right after its sender was visited.
+                    emitted = False
                     for i, s in enumerate(w_send):
-                        s.flush(emit_to_ps)
+                        emitted = bool(s.flush(emit_to_ps)) or emitted
                     for j, s in enumerate(p_send):
-                        s.flush(emit_to_worker)
-                    flushed_idle = True
+                        emitted = bool(s.flush(emit_to_worker)) or emitted
+                    flushed_idle = not emitted
                     continue
                 if idle >= self.wait_s:
                     break
