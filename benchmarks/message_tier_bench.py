@@ -26,7 +26,7 @@ def main():
     p.add_argument("--dim", type=int, default=8)
     p.add_argument("--lanes", type=int, default=16)
     p.add_argument("--capacity", type=int, default=256)
-    p.add_argument("--limit", type=int, default=4096)
+    p.add_argument("--limit", type=int, default=16384)
     p.add_argument("--iters", type=int, default=3)
     a = p.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))

@@ -625,6 +625,8 @@ struct TxnArgs {
   unsigned long long* counters;  // [0] pulls sent, [1] pushes sent, [2] answers consumed
   int self;
   int mode;
+  int per_ring_cap;       // pulls one ring may have outstanding (fair share of the credits; <= ring capacity)
+  int pad_;
 };
 
 #define TXN_WARPS 8
@@ -643,7 +645,9 @@ __global__ void __launch_bounds__(32 * TXN_WARPS)
   unsigned long long qtail_cache = 0;             // the server's tail of it, as last seen
   unsigned long long rtail = hr->tail, rtail_pub = rtail;
   int outstanding = 0;
-  const int max_out = a.resp.capacity;
+  // a ring never holds more than its share of the worker's credits: otherwise the first rings to run take
+  // them all and most server warps idle (it matters for the lock stores, whose server path is per message)
+  const int max_out = a.per_ring_cap > 0 ? min(a.per_ring_cap, a.resp.capacity) : a.resp.capacity;
   const int stride = a.req.stride;
   const bool lane_batches = stride <= FPS_BATCH_MAX_STRIDE;   // one lane moves one message
   unsigned long long n_pull = 0, n_push = 0, n_ans = 0;

@@ -40,7 +40,8 @@ class RingSetC(C.Structure):
 class TxnArgsC(C.Structure):
     _fields_ = [("req", RingSetC), ("resp", RingSetC), ("ids", C.c_void_p), ("deltas", C.c_void_p),
                 ("seg", C.c_void_p), ("out_vals", C.c_void_p), ("credits", C.c_void_p), ("err", C.c_void_p),
-                ("counters", C.c_void_p), ("self", C.c_int), ("mode", C.c_int)]
+                ("counters", C.c_void_p), ("self", C.c_int), ("mode", C.c_int), ("per_ring_cap", C.c_int),
+                ("pad_", C.c_int)]
 
 
 TXN_PULL_PUSH, TXN_PULL_ONLY, TXN_PUSH_ONLY = 0, 1, 2
@@ -212,6 +213,7 @@ class DeviceRingClient:
         dev = table.cuda_device
         self.dev, self.stride = dev, rings.stride
         self.table, self.rings = table, rings
+        self.pull_limit = int(pull_limit)
         self.txn_credits = torch.tensor([pull_limit, 0], dtype=torch.int32, device=dev)
         self.txn_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.txn_counters = torch.zeros(3, dtype=torch.int64, device=dev)
@@ -306,6 +308,8 @@ class DeviceRingClient:
             a.out_vals = out.data_ptr() if out is not None else None
             a.credits, a.err, a.counters = self.txn_credits.data_ptr(), self.txn_err.data_ptr(), self.txn_counters.data_ptr()
             a.self, a.mode = self.rings.rank, mode
+            n_rings = tab.n_shards * L
+            a.per_ring_cap = max(32, -(-self.pull_limit // n_rings))     # fair share of the credit pool
             native._check(native.lib().fps_client_txn(C.byref(a), C.c_void_p(self.stream.cuda_stream)), "client_txn")
             native._bump()
             res = None
