@@ -127,6 +127,7 @@ class CombinationLogic:
         self.condition = condition
         self.combinables = list(combinables)
         self.data: List[Any] = []
+        self._flushes = 0
         self._lock = threading.RLock()
         for c in self.combinables:
             if isinstance(c, TimerLogic):
@@ -136,6 +137,7 @@ class CombinationLogic:
         with self._lock:
             if self.condition(self.combinables) and self.data:
                 batch, self.data = self.data, []
+                self._flushes += 1
                 for c in self.combinables:
                     c.clear()
                 collect(batch)
@@ -143,8 +145,14 @@ class CombinationLogic:
     def logic(self, func: Callable[[List[Any]], None], collect: Callable[[List[Any]], None]) -> None:
         with self._lock:
             func(self.data)
+            before = self._flushes
             for c in self.combinables:
                 c.logic(func, self.checkAndSend, collect)
+            if self._flushes != before and not self.data:
+                # a trigger fired in the middle of the pass: the triggers visited after it have just
+                # accounted for a message that is already gone
+                for c in self.combinables:
+                    c.clear()
 
     def flush(self, collect: Callable[[List[Any]], None]) -> bool:
         """Unconditional flush (used at termination so no message is stranded).  Returns whether

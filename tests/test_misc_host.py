@@ -1,6 +1,8 @@
 """Offline PA pipeline, experiment CLIs, model IO, metrics, rate-replay source."""
 import random
 
+import pytest
+
 from fps_b200.models.pa.offline import PassiveAggressiveFilter, paBinaryClassificationOffline
 from fps_b200.models.pa.sparse import LegacySparseVector
 from fps_b200.models.sketch import experiments
@@ -106,3 +108,58 @@ def test_counters_prometheus_text():
     c.inc("ps_pull_rows", 10); c.inc("ps_pull_rows", 5); c.set("ring occupancy/max", 3)
     text = c.prometheus_text()
     assert "fps_b200_ps_pull_rows 15\n" in text and "fps_b200_ring_occupancy_max 3\n" in text
+
+
+# ---- round-2 host-side fixes -----------------------------------------------------------------------------------
+def test_batch_triggers_are_cleared_when_the_buffer_is_swapped_out():
+    """After a flush the next batch is measured from zero (a stale count made batches drift)."""
+    from fps_b200.protocol.combination import CombinationLogic, CountLogic, TimerLogic, any_of
+
+    got = []
+    lg = CombinationLogic(any_of, [CountLogic(3), TimerLogic(3600.0)])
+    for i in range(2):
+        lg.logic(lambda data, i=i: data.append(i), got.append)
+    assert lg.flush(got.append) is True and got == [[0, 1]]          # idle flush with 2 of 3 buffered
+    assert lg.flush(got.append) is False                               # nothing left: reports "emitted nothing"
+    for i in range(3):
+        lg.logic(lambda data, i=i: data.append(10 + i), got.append)
+    assert got == [[0, 1], [10, 11, 12]]                               # a full batch of 3, not 1
+    assert lg.combinables[1].containsData is False
+    lg.close()
+
+
+def test_seeded_mf_workers_get_their_own_random_streams():
+    from fps_b200.models.mf.online import PSOnlineMatrixFactorizationWorker
+    from fps_b200.runtime.local_engine import assign_subtask, clone_logic
+    from fps_b200.limiter import addPullLimiter
+
+    proto = addPullLimiter(PSOnlineMatrixFactorizationWorker(4, -1.0, 1.0, 0.1, 8, 0, seed=7), 10)
+    copies = [clone_logic(proto) for _ in range(3)]
+    for i, c in enumerate(copies):
+        assign_subtask(c, i, 3)
+        c.open()
+    firsts = [tuple(c.inner._factor_init().nextFactor(0)) for c in copies]
+    assert len(set(firsts)) == 3                                       # identical seeds used to give identical vectors
+    again = clone_logic(proto); assign_subtask(again, 1, 3); again.open()
+    assert tuple(again.inner._factor_init().nextFactor(0)) == firsts[1]   # still deterministic per subtask
+
+
+def test_native_pa_rejects_malformed_csr():
+    import numpy as np
+    from fps_b200.ops import host
+
+    with pytest.raises(ValueError):
+        host.pa_binary([0, 2], [0, 1], [1.0, 1.0], [1, -1], 4)        # row_ptr needs n + 1 entries
+    with pytest.raises(ValueError):
+        host.pa_binary([0, 1, 3], [0, 1], [1.0, 1.0], [1, -1], 4)     # row_ptr[-1] != nnz
+
+
+def test_synthetic_low_rank_ratings_are_a_pure_function_of_the_ids():
+    import torch
+    from fps_b200.utils.synthetic import lowrank_ratings
+
+    u = torch.randint(0, 10_000_000, (50_000,)); i = torch.randint(0, 1_000_000, (50_000,))
+    r = lowrank_ratings(u, i)
+    assert torch.equal(r, lowrank_ratings(u.clone(), i.clone()))
+    assert abs(float(r.mean())) < 0.02 and abs(float(r.std()) - 0.5) < 0.02
+    assert not torch.equal(r, lowrank_ratings(u, i, seed=1))
