@@ -399,10 +399,10 @@ def test_replica_flush_policy_count_timer_any_all_on_device(dev):
     rc = ReplicaCache(t, flush_count=10 ** 9, sync_interval_ms=20, stagger=False, own_inplace=False)   # timer only
     rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [0]
     time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
-    rc = ReplicaCache(t, flush_count=2, sync_interval_ms=20, require="all", stagger=False, own_inplace=False)
+    rc = ReplicaCache(t, flush_count=2, sync_interval_ms=250, require="all", stagger=False, own_inplace=False)
     rc.after_step(1); rc.after_step(1); torch.cuda.synchronize()
     assert rc.flush_counts() == [0]                             # count reached, deadline not yet
-    time.sleep(0.03); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
+    time.sleep(0.3); rc.after_step(1); torch.cuda.synchronize(); assert rc.flush_counts() == [1]
     # a local update reaches the master on flush, and only then
     ids = torch.tensor([7], device=dev)
     before = t.pull(ids)[0, :16].clone()
