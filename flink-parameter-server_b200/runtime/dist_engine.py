@@ -5,10 +5,12 @@ Rank r hosts worker r and PS shard r (``workerParallelism == psParallelism == wo
 job advances in rounds; in every round each rank
 
   1. feeds up to ``records_per_round`` local input records to ``workerLogic.onRecv``,
-  2. exchanges the produced worker->PS messages (bucketed by ``paramPartitioner``), lets its PS shard
-     handle them (``onPullRecv`` / ``onPushRecv``),
-  3. exchanges the PS->worker answers (bucketed by ``wInPartition``) and delivers them
-     (``onPullRecv``), whose pushes / pulls travel in the next round.
+  2. takes part in ONE exchange that carries both directions -- the worker->PS messages produced since the
+     last round (bucketed by ``paramPartitioner``), the PS->worker answers produced in the last round
+     (bucketed by ``wInPartition``) and the termination status,
+  3. lets its PS shard handle the received requests (``onPullRecv`` / ``onPushRecv``; the answers travel in
+     the next round) and delivers the received answers (``onPullRecv``; its pushes / pulls travel in the next
+     round).
 
 Message lists keep their order, so delivery is FIFO per (producer, consumer) pair like Flink's
 channels.  The job ends when every rank is out of input and a full round moved no message (the
@@ -28,23 +30,18 @@ from .stream import ResultStream
 from .transform import default_param_partitioner, default_worker_partitioner
 
 
-def _exchange(buckets: List[List[Any]], group) -> List[Any]:
-    """buckets[d] = messages for rank d.  Returns the messages addressed to this rank, ordered by
-    source rank then send order."""
+def _exchange(payload: Any, group) -> List[Any]:
+    """One pickled all-gather per round: every rank's ``payload`` (its per-destination buckets + status)."""
     world = dist.get_world_size(group)
-    gathered: List[Optional[List[List[Any]]]] = [None] * world
-    dist.all_gather_object(gathered, buckets, group=group)
-    me = dist.get_rank(group)
-    out: List[Any] = []
-    for src in range(world):
-        out.extend(gathered[src][me])
-    return out
+    gathered: List[Any] = [None] * world
+    dist.all_gather_object(gathered, payload, group=group)
+    return gathered
 
 
 def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
                           paramPartitioner: Optional[Callable[[Any], int]] = None,
                           wInPartition: Optional[Callable[[Any], int]] = None, group=None,
-                          records_per_round: int = 256, gather_results: bool = True) -> ResultStream:
+                          records_per_round: int = 1024, gather_results: bool = True) -> ResultStream:
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     part = paramPartitioner or default_param_partitioner(world)
     wpart = wInPartition or default_worker_partitioner(world)
@@ -82,6 +79,9 @@ def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
     psLogic.open({}, RuntimeContext(rank, world))
     it = iter(local_data)
     exhausted = False
+    on_pull = lambda id, widx: psLogic.onPullRecv(id, widx, server)
+    on_push = lambda id, delta: psLogic.onPushRecv(id, delta, server)
+    on_answer = lambda a: workerLogic.onPullRecv(a.paramId, a.param, client)
     while True:
         fed = 0
         while not exhausted and fed < records_per_round:
@@ -91,17 +91,18 @@ def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
             except StopIteration:
                 exhausted = True
         out_ps, to_ps[:] = list(to_ps), [[] for _ in range(world)]
-        n_moved = sum(len(b) for b in out_ps)
-        for m in _exchange(out_ps, group):
-            p_recv.onWorkerMsg(m, lambda id, widx: psLogic.onPullRecv(id, widx, server),
-                               lambda id, delta: psLogic.onPushRecv(id, delta, server))
         out_w, to_worker[:] = list(to_worker), [[] for _ in range(world)]
-        n_moved += sum(len(b) for b in out_w)
-        for m in _exchange(out_w, group):
-            w_recv.onPullAnswerRecv(m, lambda a: workerLogic.onPullRecv(a.paramId, a.param, client))
-        status = [None] * world
-        dist.all_gather_object(status, (exhausted, n_moved, sum(len(b) for b in to_ps)), group=group)
-        if all(s[0] and s[1] == 0 and s[2] == 0 for s in status):
+        n_moved = sum(len(b) for b in out_ps) + sum(len(b) for b in out_w)
+        gathered = _exchange((out_ps, out_w, exhausted, n_moved), group)
+        for src in range(world):                      # FIFO per (producer, consumer) pair
+            for m in gathered[src][0][rank]:
+                p_recv.onWorkerMsg(m, on_pull, on_push)
+        for src in range(world):
+            for m in gathered[src][1][rank]:
+                w_recv.onPullAnswerRecv(m, on_answer)
+        # every rank sees the same statuses: stop when all inputs are exhausted and the round carried nothing
+        # (then nothing was delivered anywhere, so no rank holds a message produced by this round either)
+        if all(g[2] and g[3] == 0 for g in gathered):
             break
     workerLogic.close()
     psLogic.close(server)
