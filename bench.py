@@ -67,6 +67,8 @@ def parse():
     p.add_argument("--no-direct", action="store_true", help="skip the direct one-sided mode measurement (N > 1)")
     p.add_argument("--no-fp64", action="store_true",
                    help="skip the fp64 row (the reference's precision: Array[Double] factors)")
+    p.add_argument("--no-numa-bind", action="store_true",
+                   help="do not bind the process to the NUMA node of its GPU (utils/numa.py)")
     p.add_argument("--kernel", default=None, choices=[None, "tma", "reg"],
                    help="fused MF kernel variant (default: reg = register-staged loads at full occupancy)")
     return p.parse_args()
@@ -234,6 +236,17 @@ def main():
     n_dev = torch.cuda.device_count()
     shared_gpu = world > 1 and (os.environ.get("FPS_SHARE_GPU") == "1" or n_dev < world)
     local_rank = local_rank % max(n_dev, 1) if shared_gpu else local_rank
+    # torchrun does not place its children: put this worker (and the pinned buffers it allocates below) on the
+    # NUMA node of its GPU, so the per-step H2D copies do not cross the inter-socket link (best effort, no-op
+    # on a single-node box or with FPS_NUMA_BIND=0)
+    numa_info = None
+    if not a.no_numa_bind:
+        try:
+            from fps_b200.utils.numa import bind_to_gpu_node
+
+            numa_info = bind_to_gpu_node(local_rank)
+        except Exception as exc:      # placement is an optimisation, never a reason to fail
+            numa_info = {"error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     saved_stdout = os.dup(1)
@@ -434,6 +447,7 @@ def main():
                                      "sliced": model.replica.sliced, "own_shard_in_place": model.replica.own is not None,
                                      "kernel_ms": model.replica.timing_summary()}
                                     if getattr(model, "replica", None) is not None else None),
+                       "host_placement": numa_info,
                        "quality": quality},
             "value_direct": direct,
             "value_fp64": fp64,

@@ -163,3 +163,42 @@ def test_synthetic_low_rank_ratings_are_a_pure_function_of_the_ids():
     assert torch.equal(r, lowrank_ratings(u.clone(), i.clone()))
     assert abs(float(r.mean())) < 0.02 and abs(float(r.std()) - 0.5) < 0.02
     assert not torch.equal(r, lowrank_ratings(u, i, seed=1))
+
+
+def test_numa_binding_is_best_effort_and_restricts_to_the_gpu_node(tmp_path):
+    import os
+
+    from fps_b200.utils import numa
+
+    assert numa.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa.parse_cpulist("") == set()
+    # no GPU / no sysfs entry: nothing happens
+    assert numa.bind_to_node(None)["bound"] is False
+    assert numa.gpu_numa_node(0, pci_root=str(tmp_path)) is None
+    before = os.sched_getaffinity(0)
+    cpus = sorted(before)
+    if len(cpus) < 4:
+        return
+    half = len(cpus) // 2
+    for n, part in enumerate((cpus[:half], cpus[half:])):
+        d = tmp_path / f"node{n}"
+        d.mkdir()
+        (d / "cpulist").write_text(",".join(str(c) for c in part) + "\n")
+    try:
+        info = numa.bind_to_node(1, node_root=str(tmp_path), set_policy=False)
+        assert info["bound"] and info["cpus"] == len(cpus) - half
+        assert os.sched_getaffinity(0) == set(cpus[half:])
+        # a node whose CPUs are outside the allowed set leaves the placement alone
+        (tmp_path / "node1" / "cpulist").write_text("100000-100003\n")
+        info = numa.bind_to_node(1, node_root=str(tmp_path), set_policy=False)
+        assert not info["bound"] and os.sched_getaffinity(0) == set(cpus[half:])
+    finally:
+        os.sched_setaffinity(0, before)
+    # single-node box (this container's real sysfs): no-op
+    assert numa.bind_to_node(0)["bound"] is False or len(os.listdir("/sys/devices/system/node")) > 1
+    os.sched_setaffinity(0, before)
+    os.environ["FPS_NUMA_BIND"] = "0"
+    try:
+        assert numa.bind_to_gpu_node(0)["why"] == "FPS_NUMA_BIND=0"
+    finally:
+        del os.environ["FPS_NUMA_BIND"]
