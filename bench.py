@@ -315,11 +315,14 @@ def main():
     e0.record()
     for s in range(a.steps):
         model.step(*devb[(a.warmup + s) % len(devb)])
+    e_mid = torch.cuda.Event(enable_timing=True)
+    e_mid.record()
     if hasattr(model, "flush"):
         model.flush()          # item-cache mode: the timed region includes every delta merge
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    merge_ms = e_mid.elapsed_time(e1)      # end-of-run merge of the replica mode (inside the timed region)
     launches = native.launch_count() - launches0
     windows.append((w0, time.time()))
     barrier()
@@ -445,7 +448,11 @@ def main():
                        "precision_note": "fp32 tables and math (reference: fp64 on the JVM)",
                        "exchange": ({"ctas": model.replica.n_ctas, "stages": model.replica.stages,
                                      "sliced": model.replica.sliced, "own_shard_in_place": model.replica.own is not None,
-                                     "kernel_ms": model.replica.timing_summary()}
+                                     "kernel_ms": model.replica.timing_summary(),
+                                     "final_merge_ms": merge_ms,
+                                     "final_merge_note": "the timed region ends with a full (all slices, all "
+                                                         "destinations) delta merge that is not overlapped with "
+                                                         "training; rank 0's device time of it, included in value"}
                                     if getattr(model, "replica", None) is not None else None),
                        "host_placement": numa_info,
                        "quality": quality},
