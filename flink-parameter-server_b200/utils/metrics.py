@@ -64,6 +64,73 @@ class NDCGSink:
                 f.write(",".join(str(x) for x in row) + "\n")
 
 
+class nDCGSink:
+    """The reference's evaluation sink with its file formats (T/matrix/factorization/sink/nDCGSink.scala:192-272):
+    consumes ``(itemId, timestamp, [(score, itemId)])`` records, scores the rank of the rated item in the
+    list (``nDCG = ln 2 / ln(1 + rank)``, 0 if absent), and on ``close()`` writes either the human-readable
+    block format or CSV -- ``invokes,avgnDCG,hitrate`` (no periods) / one ``period,invokes,avgnDCG,hitrate``
+    line per period of ``periodLength`` timestamp units."""
+
+    def __init__(self, fileName: str, periodLength: int = 86400, append: bool = False, csv: bool = False):
+        self.fileName, self.periodLength, self.append, self.csv = fileName, int(periodLength), append, csv
+        self.sumnDCG, self.counter, self.hit = 0.0, 0, 0
+        self.perDay: Dict[int, List[float]] = {}
+
+    def invoke(self, value) -> None:
+        item, timestamp, topk = value[-3], value[-2], value[-1]       # 3-tuples, or 4-tuples led by the user id
+        g = 0.0
+        for rank, (_score, it) in enumerate(topk, start=1):
+            if it == item:
+                g = math.log(2.0) / math.log(1.0 + rank)
+                break
+        self.hit += int(g != 0.0)
+        self.sumnDCG += g
+        self.counter += 1
+        if self.periodLength > 0:
+            d = self.perDay.setdefault(int(timestamp // self.periodLength), [0, 0.0, 0])
+            d[0] += 1; d[1] += g; d[2] += int(g != 0.0)
+
+    def close(self) -> None:
+        avg = self.sumnDCG / self.counter if self.counter else float("nan")
+        with open(self.fileName, "a" if self.append else "w") as f:
+            if self.csv:
+                if self.periodLength <= 0:
+                    f.write(f"{self.counter},{avg},{self.hit / self.counter if self.counter else float('nan')}\n")
+            else:
+                f.write(f"Number of invokes: {self.counter}\nSum nDCG: {self.sumnDCG}\nAvg nDCG: {avg}\n"
+                        f"Hit: {self.hit}\n\n")
+            if self.periodLength > 0:
+                for day in sorted(self.perDay):
+                    inv, tot, hit = self.perDay[day]
+                    if self.csv:
+                        f.write(f"{day},{inv},{tot / inv},{hit / inv}\n")
+                    else:
+                        f.write(f"Period {day}\n\t:Number of invokes: {inv}\n\t:Sum nDCG: {tot}\n"
+                                f"\t:Avg nDCG: {tot / inv}\n\t:Hit: {hit}\n\n")
+
+
+def _drain(topK, sink: nDCGSink) -> nDCGSink:
+    for rec in topK:
+        sink.invoke(rec)
+    sink.close()
+    return sink
+
+
+def nDCGToFile(topK, fileName: str, periodLength: int = 0) -> nDCGSink:
+    """Human-readable totals (+ per-period blocks when ``periodLength > 0``), nDCGSink.scala:42-80."""
+    return _drain(topK, nDCGSink(fileName, periodLength, False, False))
+
+
+def nDCGToCsv(topK, fileName: str) -> nDCGSink:
+    """Appends one ``invokes,avgnDCG,hitrate`` line (nDCGSink.scala:91-108)."""
+    return _drain(topK, nDCGSink(fileName, 0, True, True))
+
+
+def nDCGPeriodsToCsv(topK, fileName: str, periodLength: int, append: bool = False) -> nDCGSink:
+    """One ``period,invokes,avgnDCG,hitrate`` line per period (nDCGSink.scala:123-147)."""
+    return _drain(topK, nDCGSink(fileName, periodLength, append, True))
+
+
 class Counters:
     """Thread-safe named counters / gauges (pulls, pushes, credit stalls, ring occupancy, ...)."""
 
