@@ -2,6 +2,8 @@
 (T/passive/aggressive/PassiveAggressiveParameterServerTest.scala:44-100: accuracy >= 80 %, scaled down)."""
 import random
 
+import pytest
+
 import numpy as np
 
 from fps_b200.api import Left, Right
@@ -66,6 +68,14 @@ def test_binary_pa_accuracy_gate_range_partitioning_3x3():
     model = dict(out.ps_outputs())
     acc = sum((v.dot(model) > 0) == y for v, y in data[:20]) / 20
     assert acc >= 0.8, acc
+    # the reference's evaluation helper (percent; refuses unlabelled examples)
+    from fps_b200.models.pa.evaluation import PassiveAggressiveBinaryModelEvaluation as Ev
+    pac = PassiveAggressiveBinaryAlgorithm.buildPA()
+    assert abs(Ev.accuracy(model, data[:20], feats, pac) - 100.0 * acc) < 1e-9
+    c = Ev.confusion(model, data[:20], pac)
+    assert sum(c.values()) == 20 and c["tt"] + c["ff"] == round(acc * 20)
+    with pytest.raises(ValueError):
+        Ev.accuracy(model, [(data[0][0], None)], feats, pac)
     # predict path with the trained model loaded back through transformWithModelLoad
     pred = transformBinary(list(model.items()))([Right((i, v)) for i, (v, _) in enumerate(data[:20])],
                                                 3, 3, PassiveAggressiveBinaryAlgorithm.buildPA(), 500,
@@ -89,6 +99,8 @@ def test_multiclass_pa_with_long_ids():
     model = dict(out.ps_outputs())
     acc = sum(algo.predict(v, model) == y for v, y in data[:50]) / 50
     assert acc >= 0.7, acc
+    from fps_b200.models.pa.evaluation import PassiveAggressiveMultiModelEvaluation as EvM
+    assert abs(EvM.accuracy(model, data[:50], feats, algo) - 100.0 * acc) < 1e-9
     pred = transformMulticlassWithLongId(list(model.items()))(
         [Right((1000 + i, v)) for i, (v, _) in enumerate(data[:10])], 2, 2, algo, 100, L, feats, False, 200)
     ids = sorted(i for i, _ in pred.worker_outputs())
