@@ -244,7 +244,7 @@ def main():
         try:
             from fps_b200.utils.numa import bind_to_gpu_node
 
-            numa_info = bind_to_gpu_node(local_rank)
+            numa_info = bind_to_gpu_node(local_rank, min_cpus=8)   # fewer local CPUs: memory policy only
         except Exception as exc:      # placement is an optimisation, never a reason to fail
             numa_info = {"error": f"{type(exc).__name__}: {exc}"}
     torch.cuda.set_device(local_rank)
