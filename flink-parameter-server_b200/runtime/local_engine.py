@@ -19,6 +19,7 @@ It is also the semantic oracle for the device tier's tests.
 from __future__ import annotations
 
 import copy
+import os
 import queue
 import threading
 import time
@@ -27,10 +28,12 @@ from typing import Any, Callable, List, Optional
 from ..api import (Left, LooseParameterServerLogic, LooseWorkerLogic, ParameterServer,
                    ParameterServerClient, Right, RuntimeContext)
 from ..protocol.messages import PullAnswer
-from ..protocol.senders import PSReceiver, PSSender, WorkerReceiver, WorkerSender
+from ..parallel.partitioner import stable_hash
+from ..protocol.senders import (PSReceiver, PSSender, SimplePSReceiver, SimplePSSender, SimpleWorkerReceiver,
+                                SimpleWorkerSender, WorkerReceiver, WorkerSender)
 from .stream import DataStream, ResultStream, as_stream
 
-_DATA, _ANSWER, _REQ, _STOP = 0, 1, 2, 3
+_DATA, _ANSWER, _REQ, _STOP, _PULL, _PUSH = 0, 1, 2, 3, 4, 5
 
 
 def assign_subtask(obj: Any, index: int, parallelism: int, depth: int = 0) -> None:
@@ -87,12 +90,18 @@ class _Activity:
         return s
 
     def add(self, n: int = 1) -> None:
-        s = self._slot()
+        try:
+            s = self._local.slot
+        except AttributeError:
+            s = self._slot()
         s[0] += n
         s[2] = time.monotonic()
 
     def done(self, n: int = 1) -> None:
-        s = self._slot()
+        try:
+            s = self._local.slot
+        except AttributeError:
+            s = self._slot()
         s[1] += n
         s[2] = time.monotonic()
 
@@ -148,8 +157,11 @@ class MessagingPS(ParameterServer):
 
 class LocalEngine:
     def __init__(self, workerParallelism: int, psParallelism: int, iterationWaitTime: float,
-                 call_worker_open: bool = True, ps_batch: int = 4096):
+                 call_worker_open: bool = True, ps_batch: int = 4096, fast_path: Optional[bool] = None):
         self.ps_batch = max(1, int(ps_batch))
+        # stock protocol (Simple sender / receivers, default partitioners): route by id and queue plain records,
+        # no message objects (same observable behaviour; FPS_ENGINE_FAST=0 forces the general path)
+        self.fast_path = (os.environ.get("FPS_ENGINE_FAST", "1") != "0") if fast_path is None else bool(fast_path)
         self.wP = int(workerParallelism)
         self.psP = int(psParallelism)
         self.wait_s = max(0.0, float(iterationWaitTime) / 1000.0)
@@ -201,6 +213,51 @@ class LocalEngine:
                 s.bind_partitioner(lambda m: int(wInPartition(m)))
         clients = [MessagingPSClient(w_send[i], i, emit_to_ps, emit_output) for i in range(self.wP)]
         servers = [MessagingPS(p_send[j], emit_to_worker, emit_output) for j in range(self.psP)]
+        fast = (self.fast_path and type(workerSender) is SimpleWorkerSender
+                and type(workerReceiver) is SimpleWorkerReceiver and type(psSender) is SimplePSSender
+                and type(psReceiver) is SimplePSReceiver
+                and getattr(paramPartitioner, "fps_default", None) == "hash"
+                and getattr(wInPartition, "fps_default", None) == "worker_index")
+        self.used_fast_path = fast
+        if fast:
+            psP, wP, add = self.psP, self.wP, act.add
+            ps_put = [q.put for q in ps_inbox]
+            w_put = [q.put for q in w_inbox]
+
+            class FastClient(ParameterServerClient):       # MessagingPSClient + SimpleWorkerSender + hash routing
+                __slots__ = ("partitionId",)
+
+                def __init__(self, partitionId: int):
+                    self.partitionId = partitionId
+
+                def pull(self, id) -> None:
+                    dest = stable_hash(id) % psP
+                    add()
+                    ps_put[dest]((_PULL, id, self.partitionId))
+
+                def push(self, id, deltaUpdate) -> None:
+                    dest = stable_hash(id) % psP
+                    add()
+                    ps_put[dest]((_PUSH, id, deltaUpdate))
+
+                def output(self, out) -> None:
+                    emit_output(Left(out))
+
+            class FastServer(ParameterServer):             # MessagingPS + SimplePSSender + worker-index routing
+                __slots__ = ()
+
+                def answerPull(self, id, value, workerPartitionIndex) -> None:
+                    dest = int(workerPartitionIndex)
+                    if not 0 <= dest < wP:
+                        raise RuntimeError("Pull answer key should be the partition ID itself!")
+                    add()
+                    w_put[dest]((_ANSWER, id, value))
+
+                def output(self, out) -> None:
+                    emit_output(Right(out))
+
+            clients = [FastClient(i) for i in range(self.wP)]
+            servers = [FastServer() for _ in range(self.psP)]
 
         def fail(e: BaseException) -> None:
             with act.lock:
@@ -229,6 +286,67 @@ class LocalEngine:
                             on_answer_msg(payload, on_answer)
                     finally:
                         done()
+            except BaseException as e:  # noqa: BLE001
+                fail(e)
+
+        def worker_loop_fast(i: int) -> None:
+            logic, client = w_logic[i], clients[i]
+            try:
+                inbox_get, done = w_inbox[i].get, act.done
+                if self.call_worker_open:
+                    logic.open()
+                on_recv, on_pull_recv = logic.onRecv, logic.onPullRecv
+                while True:
+                    item = inbox_get()
+                    kind = item[0]
+                    if kind == _STOP:
+                        break
+                    try:
+                        if kind == _ANSWER:
+                            on_pull_recv(item[1], item[2], client)
+                        else:
+                            on_recv(item[1], client)
+                    finally:
+                        done()
+            except BaseException as e:  # noqa: BLE001
+                fail(e)
+
+        def ps_loop_fast(j: int) -> None:
+            logic, server = p_logic[j], servers[j]
+            inbox = ps_inbox[j]
+            try:
+                inbox_get, done = inbox.get, act.done
+                logic.open({}, RuntimeContext(j, self.psP))
+                on_pull, on_push = logic.onPullRecv, logic.onPushRecv
+                flush = getattr(logic, "flush", None)
+                stop = False
+                while not stop:
+                    item = inbox_get()
+                    if item[0] == _STOP:
+                        break
+                    n = 1
+                    try:
+                        if item[0] == _PULL:
+                            on_pull(item[1], item[2], server)
+                        else:
+                            on_push(item[1], item[2], server)
+                        if flush is not None:
+                            while n < self.ps_batch:
+                                try:
+                                    item = inbox.get_nowait()
+                                except queue.Empty:
+                                    break
+                                if item[0] == _STOP:
+                                    stop = True
+                                    break
+                                n += 1
+                                if item[0] == _PULL:
+                                    on_pull(item[1], item[2], server)
+                                else:
+                                    on_push(item[1], item[2], server)
+                            flush(server)
+                    finally:
+                        done(n)
             except BaseException as e:  # noqa: BLE001
                 fail(e)
 
@@ -306,10 +424,10 @@ class LocalEngine:
                 with act.lock:
                     act.sources_open -= 1
 
-        threads = [threading.Thread(target=worker_loop, args=(i,), daemon=True, name=f"fps-worker-{i}")
-                   for i in range(self.wP)]
-        threads += [threading.Thread(target=ps_loop, args=(j,), daemon=True, name=f"fps-ps-{j}")
-                    for j in range(self.psP)]
+        threads = [threading.Thread(target=worker_loop_fast if fast else worker_loop, args=(i,), daemon=True,
+                                    name=f"fps-worker-{i}") for i in range(self.wP)]
+        threads += [threading.Thread(target=ps_loop_fast if fast else ps_loop, args=(j,), daemon=True,
+                                     name=f"fps-ps-{j}") for j in range(self.psP)]
         feeders = [threading.Thread(target=feed, args=(s,), daemon=True, name=f"fps-src-{k}")
                    for k, s in enumerate(stream.sources)]
         for t in threads + feeders:

@@ -50,6 +50,7 @@ def default_param_partitioner(psParallelism: int) -> Callable[[Any], int]:
         m = _first(msg)
         return stable_hash(m.paramId) % psParallelism
 
+    part.fps_default = "hash"        # lets the engine route by id without building a message (local_engine.py)
     return part
 
 
@@ -57,6 +58,7 @@ def default_worker_partitioner(workerParallelism: int) -> Callable[[Any], int]:
     def part(msg) -> int:
         return _first(msg).workerPartitionIndex
 
+    part.fps_default = "worker_index"
     return part
 
 

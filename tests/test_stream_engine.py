@@ -124,3 +124,57 @@ def test_per_subtask_copies_and_ctor_fork():
 
     with pytest.raises(TypeError):
         transform([1], NotCopyable(), NoPS(), 2, 1, 50)
+
+
+def test_stock_protocol_fast_path_equals_the_general_path(monkeypatch):
+    """Stock senders / receivers + default partitioners are routed by id with plain queue records (no message
+    objects); the observable behaviour is the general path's."""
+    from fps_b200 import WorkerLogic, addPullLimiter, transform
+    from fps_b200.protocol.senders import SimpleWorkerSender
+    from fps_b200.runtime.transform import default_param_partitioner, default_worker_partitioner
+    from fps_b200.server.logics import SimplePSLogic
+
+    class W(WorkerLogic):
+        def onRecv(self, data, ps):
+            ps.pull(data)
+
+        def onPullRecv(self, id, value, ps):
+            ps.push(id, 1)
+            ps.output((id, value))
+
+    def run(wp, pp, **kw):
+        data = [i % 37 for i in range(600)]
+        out = transform(data, addPullLimiter(W(), 8), lambda id: 10 * id, lambda p, d: p + d, wp, pp, 50, **kw)
+        return out
+
+    monkeypatch.setenv("FPS_ENGINE_FAST", "1")
+    a = run(1, 1)
+    assert a.engine.used_fast_path
+    monkeypatch.setenv("FPS_ENGINE_FAST", "0")
+    b = run(1, 1)
+    assert not b.engine.used_fast_path
+    want = {k: 10 * k + len([i for i in range(600) if i % 37 == k]) for k in range(37)}
+
+    def final(out):
+        f = {}
+        for k, v in out.ps_outputs():
+            f[k] = max(f.get(k, v), v)
+        return f
+
+    # (thread interleaving decides the order of the result stream on either path; the content is fixed)
+    assert final(a) == final(b) == want
+    assert sorted(a.ps_outputs()) == sorted(b.ps_outputs())
+    assert len(list(a.worker_outputs())) == len(list(b.worker_outputs())) == 600
+    monkeypatch.setenv("FPS_ENGINE_FAST", "1")
+    c = run(4, 3)
+    assert c.engine.used_fast_path and final(c) == want
+    # anything non-stock takes the general path
+    class MySender(SimpleWorkerSender):
+        pass
+
+    d = transform([1, 2, 3], W(), SimplePSLogic(lambda id: 0, lambda p, q: p + q), default_param_partitioner(2),
+                  default_worker_partitioner(2), 2, 2, None, MySender(), None, None, 50)
+    assert not d.engine.used_fast_path and len(list(d.ps_outputs())) == 3
+    e = transform([1, 2, 3], W(), SimplePSLogic(lambda id: 0, lambda p, q: p + q), lambda m: m.paramId % 2,
+                  default_worker_partitioner(2), 2, 2, iterationWaitTime=50)
+    assert not e.engine.used_fast_path and len(list(e.ps_outputs())) == 3
