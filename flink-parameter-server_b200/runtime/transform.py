@@ -92,8 +92,11 @@ def transform_general(trainingData, workerLogic: LooseWorkerLogic,
                       workerParallelism: int, psParallelism: int, workerReceiver, workerSender,
                       psReceiver, psSender, iterationWaitTime: float = DEFAULT_ITERATION_WAIT_TIME,
                       call_worker_open: bool = True) -> ResultStream:
+    # device-resident stores keep the general engine path (the one validated on the GPU); host stores with the
+    # stock protocol take the engine's fast path
+    on_device = type(psLogic).__name__ == "DeviceStoreLogic" and not getattr(psLogic, "emulate", False)
     engine = LocalEngine(workerParallelism, psParallelism, iterationWaitTime,
-                         call_worker_open=call_worker_open)
+                         call_worker_open=call_worker_open, fast_path=False if on_device else None)
     out = engine.run(trainingData, workerLogic, psLogic, paramPartitioner, wInPartition,
                      workerReceiver, workerSender, psReceiver, psSender)
     out.engine = engine
