@@ -27,6 +27,7 @@ from ..api import Left, ParameterServer, ParameterServerClient, Right, RuntimeCo
 from ..protocol.senders import (SimplePSReceiver, SimplePSSender, SimpleWorkerReceiver,
                                 SimpleWorkerSender)
 from .stream import ResultStream
+from ..parallel.partitioner import stable_hash
 from .transform import default_param_partitioner, default_worker_partitioner
 
 
@@ -74,7 +75,31 @@ def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
         def output(self, out):
             results.append(Right(out))
 
-    client, server = Client(), Server()
+    # default routing (hash of the id / worker index): plain tuples on the wire instead of message objects --
+    # (0, id, worker) = pull, (1, id, delta) = push, (id, value) = answer; cheaper to build, route and pickle
+    fast = paramPartitioner is None and wInPartition is None
+
+    class FastClient(ParameterServerClient):
+        def pull(self, id):
+            to_ps[stable_hash(id) % world].append((0, id, rank))
+
+        def push(self, id, deltaUpdate):
+            to_ps[stable_hash(id) % world].append((1, id, deltaUpdate))
+
+        def output(self, out):
+            results.append(Left(out))
+
+    class FastServer(ParameterServer):
+        def answerPull(self, id, value, workerPartitionIndex):
+            d = int(workerPartitionIndex)
+            if not 0 <= d < world:
+                raise RuntimeError("Pull answer key should be the partition ID itself!")
+            to_worker[d].append((id, value))
+
+        def output(self, out):
+            results.append(Right(out))
+
+    client, server = (FastClient(), FastServer()) if fast else (Client(), Server())
     workerLogic.open()
     psLogic.open({}, RuntimeContext(rank, world))
     it = iter(local_data)
@@ -95,11 +120,22 @@ def transform_distributed(local_data: Iterable[Any], workerLogic, psLogic,
         n_moved = sum(len(b) for b in out_ps) + sum(len(b) for b in out_w)
         gathered = _exchange((out_ps, out_w, exhausted, n_moved), group)
         for src in range(world):                      # FIFO per (producer, consumer) pair
-            for m in gathered[src][0][rank]:
-                p_recv.onWorkerMsg(m, on_pull, on_push)
+            if fast:
+                for m in gathered[src][0][rank]:
+                    if m[0] == 0:
+                        psLogic.onPullRecv(m[1], m[2], server)
+                    else:
+                        psLogic.onPushRecv(m[1], m[2], server)
+            else:
+                for m in gathered[src][0][rank]:
+                    p_recv.onWorkerMsg(m, on_pull, on_push)
         for src in range(world):
-            for m in gathered[src][1][rank]:
-                w_recv.onPullAnswerRecv(m, on_answer)
+            if fast:
+                for m in gathered[src][1][rank]:
+                    workerLogic.onPullRecv(m[0], m[1], client)
+            else:
+                for m in gathered[src][1][rank]:
+                    w_recv.onPullAnswerRecv(m, on_answer)
         # every rank sees the same statuses: stop when all inputs are exhausted and the round carried nothing
         # (then nothing was delivered anywhere, so no rank holds a message produced by this round either)
         if all(g[2] and g[3] == 0 for g in gathered):
